@@ -1,0 +1,66 @@
+/* skred_b200_shim.h — the entry points the drop-in ADDS to skred's synth.h.
+ *
+ * The drop-in library (libskred_shim_v<VOICE_MAX>.so, built from
+ * skred_b200/csrc/synth_shim.c against a skred source tree) defines every
+ * array of synth.def:1-89 and every function of synth.h:8-85 with the
+ * reference's names, arguments and return codes (100 = invalid voice / value,
+ * 101 = frequency out of range; synth.c:661,834,860) — those are declared by
+ * skred's own synth.h and are not repeated here.  `synth()` (synth.h:8) keeps
+ * its signature and blocks until the block is in `buffer`.
+ *
+ * Additions (SURVEY §8b "What a C-ABI replacement adds"):
+ */
+#ifndef SKRED_B200_SHIM_H
+#define SKRED_B200_SHIM_H
+
+#include "skred_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Choose device / voice shard before the first setter or synth() call
+ * (default: device $SKB_DEVICE or 0, rank 0 of 1, 8192 frames per launch).
+ * Replaces nothing in the reference (single process, no device). */
+int  skb_shim_configure(int device, int rank, int world, int max_frames);
+
+/* The engine behind the shim (created on first use; aborts if no B200). */
+skb_engine *skb_shim_engine(void);
+
+/* Push pending parameter records and device ops to the engine now (synth()
+ * does this itself at every block boundary — seq.c:170-178 granularity). */
+int  skb_shim_flush(void);
+
+/* Sticky engine error (the reference's synth() returns void). */
+int  skb_shim_last_error(void);
+
+/* Device -> host copy of the evolving state into the public arrays
+ * (voice_phase, voice_finished, voice_sample, voice_sample_hold*,
+ * voice_filter[].x1..y2, voice_amp_envelope[].is_active/sample_*,
+ * voice_smoother_gain, voice_pan_left/right) so that voice_format / `?` / `\`
+ * (synth.c:663-808) and voice_copy (synth.c:1044-1046) keep working. */
+void skb_shim_snapshot(void);
+int  skb_shim_snapshot_range(int first, int n);
+
+/* wire.c writes some arrays directly, bypassing the setters (wire.c:639-708:
+ * `h`, `s`, `J`, …).  With VOICE_MAX <= 4096 the shim diffs every voice
+ * against the last record sent at each block; above that only voices touched
+ * by a setter (or marked here) are re-packed.  skb_shim_scan_all overrides. */
+void skb_shim_mark_dirty(int voice);
+void skb_shim_scan_all(int on);
+
+/* A wave slot edited in place (wave_table_dynamic_expand, wire.c:553-586)
+ * must be re-uploaded at its next `w`. */
+void skb_shim_wave_touch(int wave);
+
+/* Split form of synth() for multi-GPU hosts: render this engine's voice shard
+ * into DEVICE memory d_mix[num_frames][2] (raw stereo sum, before the master
+ * volume of synth.c:616-620) on `stream`; after the partial mixes were summed
+ * across GPUs (ncclReduce over NVLink) the root calls skb_shim_finish. */
+int  skb_shim_render_mix(int num_frames, float *d_mix, void *stream);
+int  skb_shim_finish(const float *d_mix, int num_frames, float *out, int num_channels, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

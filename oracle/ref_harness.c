@@ -1,0 +1,171 @@
+/* oracle/ref_harness.c — TEST INFRASTRUCTURE (see oracle/README.md).
+ *
+ * Our glue, linked together with the UNMODIFIED reference translation units
+ * (synth.c wire.c seq.c skode.c amysamples.c, compiled where they lie under
+ * /root/reference by oracle/build_oracle.py) into
+ * oracle/_ref/libskred_ref_v<VOICE_MAX>.so.
+ *
+ * It provides
+ *   1. the host symbols the reference path imports from skred.c
+ *      (skred.c:38-56, 84-90; SURVEY §8b "Symbols the path imports"),
+ *   2. an offline render loop in the reference's own callback order
+ *      `synth(); seq();` (skred.c:116-119) with block = 512,
+ *   3. small accessors so Python (ctypes) can drive it.
+ *
+ * The same file, compiled with -DSKB_DROPIN, glues the reference's wire.c /
+ * seq.c / skode.c on top of the PRODUCT's synth.h implementation
+ * (skred_b200/csrc/synth_shim.c) — the drop-in proof used by tests.
+ */
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+
+#include "skred.h"
+#include "synth-types.h"
+#include "synth.h"
+#include "wire.h"
+#include "seq.h"
+#include "miniwav.h"
+#include "scope-shared.h"
+
+/* ---- 1. host symbols normally defined by skred.c ---------------------- */
+int scope_enable = 0;
+scope_buffer_t scope_safety;
+scope_buffer_t *scope = &scope_safety;
+float tempo_time_per_step = 60.0f;      /* skred.c:47 */
+float tempo_bpm = 120.0f / 4.0f;        /* skred.c:48 */
+float tempo_base = 0.0f;                /* skred.c:49 */
+int debug = 0;
+int trace = 0;
+int console_voice = 0;
+int main_running = 1;
+int rec_state = 0;                      /* skred.c:84-90 */
+long rec_ptr = 0;
+float rec_sec = (float)REC_IN_SEC;
+long rec_max = 0;
+float *recording = NULL;
+
+void util_set_thread_name(char *s) { (void)s; }
+char *udp_info(void) { return ""; }
+int udp_port = 0;
+
+/* WAV loading is outside the hot path; patches that need
+ * `:w` are not used as parity inputs. */
+float *mw_get(char *name, int *frames_out, wav_t *w, int ch) {
+  (void)name; (void)w; (void)ch;
+  if (frames_out) *frames_out = 0;
+  return NULL;
+}
+float *mw_free(float *f) { free(f); return NULL; }
+
+/* ---- 2. offline driver ------------------------------------------------- */
+static float *g_tap = NULL;
+static wire_t g_wire = WIRE();
+
+int ref_voice_max(void) { return VOICE_MAX; }
+
+/* Same order as main(): skred.c:232-236. */
+void ref_init(void) {
+  static int once = 0;
+  if (once) return;
+  once = 1;
+  /* the per-voice tap `user` must hold num_frames*VOICE_MAX*2 floats
+   * (synth.c:533-611); it is latched on the first synth() call. */
+  g_tap = (float *)calloc((size_t)SYNTH_FRAMES_PER_CALLBACK * VOICE_MAX * 2, sizeof(float));
+  synth_init();
+  wave_table_init();
+  voice_init();
+  seq_init();
+  g_wire.printf = null_printf;
+  g_wire.puts = null_puts;
+}
+
+float *ref_tap(void) { return g_tap; }
+
+/* Feed one line of skode to the reference parser (wire.c:924). */
+int ref_wire(const char *line) {
+  char buf[4096];
+  strncpy(buf, line, sizeof(buf) - 1);
+  buf[sizeof(buf) - 1] = '\0';
+  return wire(buf, &g_wire);
+}
+
+/* Load "<dir>/<n>.sk" through the reference's own sk_load (wire.c:342). */
+int ref_sk_load(const char *dir, int n) {
+  char cwd[4096];
+  if (!getcwd(cwd, sizeof(cwd))) return -1;
+  if (chdir(dir) != 0) return -2;
+  int r = sk_load(&g_wire, 0, n, 0);
+  if (chdir(cwd) != 0) return -3;
+  return r;
+}
+
+/* Render `nframes` frames as ceil(nframes/block) callbacks; returns seconds
+ * of wall time spent inside the loop (CPU baseline).  out: nframes*2 f32. */
+double ref_render(float *out, long nframes, int block, int run_seq) {
+  struct timespec a, b;
+  clock_gettime(CLOCK_MONOTONIC, &a);
+  long done = 0;
+  while (done < nframes) {
+    int n = (nframes - done) < block ? (int)(nframes - done) : block;
+    synth(out + done * 2, NULL, n, 2, g_tap);
+    if (run_seq) seq(n);
+    done += n;
+  }
+  clock_gettime(CLOCK_MONOTONIC, &b);
+  return (double)(b.tv_sec - a.tv_sec) + 1e-9 * (double)(b.tv_nsec - a.tv_nsec);
+}
+
+uint64_t ref_sample_count(void) { return synth_sample_count; }
+
+/* Install a caller-owned float table into a wave slot the way data_load does
+ * (wire.c:374-404) but with explicit loop/one-shot fields, so the dead
+ * notamy LUTs can be exercised.  The table is copied. */
+int ref_install_table(int slot, const float *data, int len, float rate,
+                      int one_shot, int loop_start, int loop_end,
+                      float midi_note, float offset_hz) {
+  if (slot < 0 || slot >= WAVE_TABLE_MAX || len <= 0) return 100;
+  float *t = (float *)malloc((size_t)len * sizeof(float));
+  memcpy(t, data, (size_t)len * sizeof(float));
+  wave_table_data[slot] = t;
+  wave_size[slot] = len;
+  wave_rate[slot] = rate;
+  wave_one_shot[slot] = one_shot;
+  wave_loop_enabled[slot] = 0;
+  wave_loop_start[slot] = loop_start;
+  wave_loop_end[slot] = loop_end;
+  wave_midi_note[slot] = midi_note;
+  wave_offset_hz[slot] = offset_hz;
+  wave_is_miniwav[slot] = 0;
+  return 0;
+}
+
+/* ---- 3. raw state access (struct fields ctypes cannot reach by symbol) -- */
+void ref_get_filter(int v, float *out9) {
+  mmf_t *f = &voice_filter[v];
+  out9[0] = f->x1; out9[1] = f->x2; out9[2] = f->y1; out9[3] = f->y2;
+  out9[4] = f->b0; out9[5] = f->b1; out9[6] = f->b2; out9[7] = f->a1; out9[8] = f->a2;
+}
+void ref_get_envelope(int v, float *f9, uint64_t *u2, int *active) {
+  envelope_t *e = &voice_amp_envelope[v];
+  f9[0] = e->a; f9[1] = e->d; f9[2] = e->s; f9[3] = e->r;
+  f9[4] = e->attack_time; f9[5] = e->decay_time; f9[6] = e->sustain_level; f9[7] = e->release_time;
+  f9[8] = e->velocity;
+  u2[0] = e->sample_start; u2[1] = e->sample_release;
+  active[0] = e->is_active;
+}
+
+/* Bring the public arrays up to date before Python reads them: a no-op for
+ * the reference (the arrays ARE the state), a device->host snapshot for the
+ * product drop-in. */
+#ifdef SKB_DROPIN
+#include "skred_b200_shim.h"
+void ref_sync_state(void) { skb_shim_snapshot(); }
+int ref_is_dropin(void) { return 1; }
+#else
+void ref_sync_state(void) {}
+int ref_is_dropin(void) { return 0; }
+#endif
