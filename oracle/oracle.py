@@ -1,0 +1,114 @@
+"""ctypes loaders for the oracle libraries.  TEST INFRASTRUCTURE (oracle/README.md).
+
+  RefSkred(V)            oracle/_ref/libskred_ref_v<V>.so — the reference's own synth.c / wire.c /
+                         seq.c / skode.c compiled with the pinned flags
+  PortSkred(V)           oracle/_build/libskred_dropin_port_v<V>.so — reference wire/seq/skode +
+                         the product's host shim rendering through the CPU restatement
+                         (oracle/skred_port.c); pins shim + port against the reference
+  DropinCuda(V)          oracle/_ref/libskred_dropin_cuda_v<V>.so — reference wire/seq/skode on
+                         top of the PRODUCT (shim + CUDA engine): the drop-in proof
+
+All three share oracle/ref_harness.c, so they are driven identically: wire()
+lines or synth.h setter calls, then `synth(); seq();` callbacks of 512 frames.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from skred_b200.host import SynthAPI, private_copy, load_engine_lib, BLOCK  # noqa: E402
+
+
+def ref_lib_path(v):
+    return os.path.join(HERE, "_ref", "libskred_ref_v%d.so" % v)
+
+
+def port_lib_path(v):
+    return os.path.join(HERE, "_build", "libskred_dropin_port_v%d.so" % v)
+
+
+def cuda_dropin_path(v):
+    return os.path.join(HERE, "_ref", "libskred_dropin_cuda_v%d.so" % v)
+
+
+class HarnessSkred(SynthAPI):
+    def __init__(self, path, voice_max, run_seq=True):
+        if not os.path.exists(path):
+            raise FileNotFoundError("%s missing: run `python oracle/build_oracle.py --voices %d`" % (path, voice_max))
+        lib = C.CDLL(private_copy(path))
+        super().__init__(lib, voice_max)
+        assert lib.ref_voice_max() == voice_max
+        lib.ref_render.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int]
+        lib.ref_render.restype = C.c_double
+        lib.ref_wire.argtypes = [C.c_char_p]
+        lib.ref_sample_count.restype = C.c_uint64
+        lib.ref_get_filter.argtypes = [C.c_int, C.c_void_p]
+        lib.ref_get_envelope.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.run_seq = 1 if run_seq else 0
+        self.cpu_seconds = 0.0
+        lib.ref_init()
+
+    def wire(self, line):
+        if isinstance(line, str):
+            line = line.encode()
+        return self.lib.ref_wire(line)
+
+    def load_lines(self, lines):
+        """What sk_load does (wire.c:342-368): one wire() per line, shared context."""
+        for ln in lines:
+            self.wire(ln)
+
+    def _synth(self, out, nframes):
+        self.cpu_seconds += self.lib.ref_render(out.ctypes.data, nframes, nframes, self.run_seq)
+
+    def sync_state(self):
+        self.lib.ref_sync_state()
+
+    def state(self):
+        """Evolving per-voice state as a dict of arrays."""
+        self.sync_state()
+        n = self.voice_max
+        filt = np.zeros((n, 9), dtype=np.float32)
+        envf = np.zeros((n, 9), dtype=np.float32)
+        envu = np.zeros((n, 2), dtype=np.uint64)
+        act = np.zeros(n, dtype=np.int32)
+        for v in range(n):
+            self.lib.ref_get_filter(v, filt[v].ctypes.data)
+            self.lib.ref_get_envelope(v, envf[v].ctypes.data, envu[v].ctypes.data, act[v:v + 1].ctypes.data)
+        return {
+            "phase": self.array("voice_phase").copy(),
+            "finished": self.array("voice_finished", C.c_int).copy(),
+            "sample": self.array("voice_sample").copy(),
+            "sh_hold": self.array("voice_sample_hold").copy(),
+            "sh_count": self.array("voice_sample_hold_count", C.c_int).copy(),
+            "filter_xy": filt[:, :4].copy(),
+            "env_active": act,
+            "env_start": envu[:, 0].copy(),
+            "env_release": envu[:, 1].copy(),
+            "smoother_gain": self.array("voice_smoother_gain").copy(),
+            "pan_left": self.array("voice_pan_left").copy(),
+            "pan_right": self.array("voice_pan_right").copy(),
+        }
+
+
+def have_ref(v=64):
+    return os.path.exists(ref_lib_path(v))
+
+
+def RefSkred(v=64, run_seq=True):
+    return HarnessSkred(ref_lib_path(v), v, run_seq)
+
+
+def PortSkred(v=64, run_seq=True):
+    return HarnessSkred(port_lib_path(v), v, run_seq)
+
+
+def DropinCuda(v=64, run_seq=True):
+    load_engine_lib()           # RTLD_GLOBAL: satisfies the private copy's DT_NEEDED
+    return HarnessSkred(cuda_dropin_path(v), v, run_seq)

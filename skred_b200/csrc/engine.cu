@@ -1,0 +1,717 @@
+/* engine.cu — the B200 voice-render engine behind include/skred_b200.h.
+ *
+ * Product code.  Built ONLY for sm_100a with the parity flags
+ *   -gencode arch=compute_100a,code=sm_100a -fmad=false -prec-div=true
+ *   -prec-sqrt=true -ftz=false -lineinfo
+ * (SURVEY H1/F5).  There is no CPU path in this file: skb_create fails with
+ * SKB_ERR_NO_DEVICE when no CUDA device of compute capability 10.x is present.
+ *
+ * Host side = a planner + uploader around the kernels of voice_kernels.cuh:
+ *   plan     voice graph -> connected components (partition.h) -> shard owner
+ *            -> SLOTS: free voices sorted by feature key (warp-homogeneous
+ *            branches), then modulation BINS (frame-lock-step CTAs)
+ *   upload   changed parameter records -> k_scatter_params (float4 SoA)
+ *   ops      ordered state edits -> k_apply_ops (block-boundary events, F8)
+ *   render   k_render_free + k_render_bins -> partial rows -> k_reduce_rows
+ *   finish   k_finish (master volume) -> pinned host -> caller's buffer
+ * Reference mapping: synth() synth.c:502-630; see DESIGN.md.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "skred_b200.h"
+#include "partition.h"
+#include "voice_kernels.cuh"
+
+#define SKB_BIN_PACK 128      /* small components are packed into bins of <= this many voices */
+#define SKB_BIN_MAX 1024      /* one CTA per bin: hard upper bound of a component */
+
+struct TableDesc { size_t off; int size; };
+
+struct skb_engine {
+  skb_config cfg;
+  int n = 0, cap = 0;
+  int err = SKB_OK;
+  char errtxt[512] = {0};
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_h2d = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  bool timing_pending = false;
+
+  /* host mirror of what the host sent */
+  std::vector<skb_voice_params> par;
+  std::vector<uint8_t> dirty;
+  std::vector<int32_t> dirty_list;
+  bool need_plan = true, planned = false;
+  bool any_noise = false;
+  std::vector<uint8_t> noise_flag;
+  int noise_count = 0;
+  cudaStream_t last_stream = nullptr;
+
+  /* plan */
+  std::vector<int32_t> comp, owner, slot_of_voice, voice_of_slot, level;
+  std::vector<int32_t> bin_of_voice;                /* -1 = free */
+  std::vector<skb_bin_desc> bins;
+  std::vector<uint64_t> edge_sig;                   /* per voice: hash of its live edges (re-plan trigger) */
+  int n_free = 0, n_free_pad = 0, n_slots = 0, n_rows = 0, n_free_rows = 0, max_bin_threads = 0;
+
+  /* device */
+  float4 *d_pq = nullptr, *d_sq[2] = {nullptr, nullptr};
+  int cur = 0;
+  float *d_tables = nullptr;
+  size_t tables_used = 0, tables_cap = 0;
+  std::vector<TableDesc> tables;
+  skb_bin_desc *d_bins = nullptr; int d_bins_cap = 0;
+  float2 *d_partials = nullptr; size_t partials_cap = 0;
+  float2 *d_mix = nullptr, *d_out = nullptr;
+  float *d_gain = nullptr, *d_noise = nullptr;
+  int *d_idx = nullptr; size_t d_idx_cap = 0;       /* slots / old_slot scratch */
+  float4 *d_recs = nullptr; size_t d_recs_cap = 0;
+  skb_op *d_ops = nullptr; size_t d_ops_cap = 0;
+  int2 *d_runs = nullptr; size_t d_runs_cap = 0;
+  skb_voice_state *d_snap = nullptr; size_t d_snap_cap = 0;
+
+  /* pinned staging */
+  float *h_gain = nullptr, *h_noise = nullptr, *h_out = nullptr;
+  int *h_idx = nullptr; size_t h_idx_cap = 0;
+  float4 *h_recs = nullptr; size_t h_recs_cap = 0;
+  skb_op *h_ops = nullptr; size_t h_ops_cap = 0;
+  int2 *h_runs = nullptr; size_t h_runs_cap = 0;
+  skb_voice_state *h_snap = nullptr; size_t h_snap_cap = 0;
+
+  std::vector<skb_op> ops;
+  skb_stats stats;
+};
+
+const char *skb_backend_name(void) { return "cuda-sm100a"; }
+
+static int fail(skb_engine *e, int code, const char *what, const char *detail = nullptr) {
+  if (e && e->err == SKB_OK) {
+    e->err = code;
+    snprintf(e->errtxt, sizeof(e->errtxt), "%s%s%s", what, detail ? ": " : "", detail ? detail : "");
+  }
+  return code;
+}
+
+#define CK(call)                                                                   \
+  do {                                                                             \
+    cudaError_t _r = (call);                                                       \
+    if (_r != cudaSuccess) return fail(e, SKB_ERR_CUDA, #call, cudaGetErrorString(_r)); \
+  } while (0)
+
+template <class T>
+static cudaError_t grow_dev(T **p, size_t *cap, size_t need) {
+  if (need <= *cap) return cudaSuccess;
+  size_t ncap = std::max(need, *cap * 2 + 64);
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  cudaError_t r = cudaMalloc((void **)p, ncap * sizeof(T));
+  *cap = (r == cudaSuccess) ? ncap : 0;
+  return r;
+}
+template <class T>
+static cudaError_t grow_pin(T **p, size_t *cap, size_t need) {
+  if (need <= *cap) return cudaSuccess;
+  size_t ncap = std::max(need, *cap * 2 + 64);
+  if (*p) cudaFreeHost(*p);
+  *p = nullptr;
+  cudaError_t r = cudaMallocHost((void **)p, ncap * sizeof(T));
+  *cap = (r == cudaSuccess) ? ncap : 0;
+  return r;
+}
+
+int skb_create(skb_engine **out, const skb_config *cfg) {
+  if (!out) return SKB_ERR_ARG;
+  *out = nullptr;
+  if (!cfg || cfg->abi_version != SKB_ABI_VERSION || cfg->n_voices <= 0 || cfg->world < 1 ||
+      cfg->rank < 0 || cfg->rank >= cfg->world)
+    return SKB_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
+    cudaGetLastError();
+    return SKB_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10) {
+    /* the fatbin holds sm_100a SASS only */
+    cudaGetLastError();
+    return SKB_ERR_NO_DEVICE;
+  }
+  skb_engine *e = new skb_engine();
+  e->cfg = *cfg;
+  if (e->cfg.max_frames < 512) e->cfg.max_frames = 512;
+  e->n = cfg->n_voices;
+  memset(&e->stats, 0, sizeof(e->stats));
+  const int n = e->n, mf = e->cfg.max_frames;
+  e->cap = ((n + 31) / 32) * 32 + 64;
+  e->par.resize(n);
+  for (int v = 0; v < n; v++) {
+    memset(&e->par[v], 0, sizeof(skb_voice_params));
+    e->par[v].table_id = -1;
+    e->par[v].freq_mod_osc = e->par[v].amp_mod_osc = e->par[v].pan_mod_osc = -1;
+  }
+  e->dirty.assign(n, 0);
+  e->noise_flag.assign(n, 0);
+  e->comp.assign(n, 0); e->owner.assign(n, 0); e->slot_of_voice.assign(n, -1);
+  e->level.assign(n, 0); e->bin_of_voice.assign(n, -1); e->edge_sig.assign(n, 0);
+  bool ok = cudaSetDevice(cfg->device) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_h2d, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreate(&e->ev_t0) == cudaSuccess && cudaEventCreate(&e->ev_t1) == cudaSuccess &&
+            cudaMalloc((void **)&e->d_pq, (size_t)SKB_NPQ * e->cap * sizeof(float4)) == cudaSuccess &&
+            cudaMalloc((void **)&e->d_sq[0], (size_t)SKB_NSQ * e->cap * sizeof(float4)) == cudaSuccess &&
+            cudaMalloc((void **)&e->d_sq[1], (size_t)SKB_NSQ * e->cap * sizeof(float4)) == cudaSuccess &&
+            cudaMalloc((void **)&e->d_mix, (size_t)mf * sizeof(float2)) == cudaSuccess &&
+            cudaMalloc((void **)&e->d_out, (size_t)mf * sizeof(float2)) == cudaSuccess &&
+            cudaMalloc((void **)&e->d_gain, (size_t)mf * sizeof(float)) == cudaSuccess &&
+            cudaMalloc((void **)&e->d_noise, (size_t)mf * sizeof(float)) == cudaSuccess &&
+            cudaMallocHost((void **)&e->h_gain, (size_t)mf * sizeof(float)) == cudaSuccess &&
+            cudaMallocHost((void **)&e->h_noise, (size_t)mf * sizeof(float)) == cudaSuccess &&
+            cudaMallocHost((void **)&e->h_out, (size_t)mf * sizeof(float2)) == cudaSuccess &&
+            cudaMemset(e->d_pq, 0, (size_t)SKB_NPQ * e->cap * sizeof(float4)) == cudaSuccess &&
+            cudaMemset(e->d_sq[0], 0, (size_t)SKB_NSQ * e->cap * sizeof(float4)) == cudaSuccess &&
+            cudaMemset(e->d_sq[1], 0, (size_t)SKB_NSQ * e->cap * sizeof(float4)) == cudaSuccess;
+  if (ok) {
+    /* the bin kernel may need more than 48 KB? no: 3*nt floats + 2*nwarps float2 <= 12.8 KB */
+    e->tables_cap = (size_t)4 << 20;
+    ok = cudaMalloc((void **)&e->d_tables, e->tables_cap * sizeof(float)) == cudaSuccess;
+  }
+  if (!ok) {
+    fprintf(stderr, "skred_b200: skb_create: %s\n", cudaGetErrorString(cudaGetLastError()));
+    skb_destroy(e);
+    return SKB_ERR_CUDA;
+  }
+  *out = e;
+  return SKB_OK;
+}
+
+void skb_destroy(skb_engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  cudaFree(e->d_pq); cudaFree(e->d_sq[0]); cudaFree(e->d_sq[1]); cudaFree(e->d_tables);
+  cudaFree(e->d_bins); cudaFree(e->d_partials); cudaFree(e->d_mix); cudaFree(e->d_out);
+  cudaFree(e->d_gain); cudaFree(e->d_noise); cudaFree(e->d_idx); cudaFree(e->d_recs);
+  cudaFree(e->d_ops); cudaFree(e->d_runs); cudaFree(e->d_snap);
+  cudaFreeHost(e->h_gain); cudaFreeHost(e->h_noise); cudaFreeHost(e->h_out); cudaFreeHost(e->h_idx);
+  cudaFreeHost(e->h_recs); cudaFreeHost(e->h_ops); cudaFreeHost(e->h_runs); cudaFreeHost(e->h_snap);
+  if (e->ev_h2d) cudaEventDestroy(e->ev_h2d);
+  if (e->ev_t0) cudaEventDestroy(e->ev_t0);
+  if (e->ev_t1) cudaEventDestroy(e->ev_t1);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int skb_last_error(const skb_engine *e) { return e ? e->err : SKB_ERR_ARG; }
+const char *skb_error_string(const skb_engine *e) { return e ? e->errtxt : "null engine"; }
+
+int skb_table_upload(skb_engine *e, const float *data, int size) {
+  if (!e || !data || size <= 0) return fail(e, SKB_ERR_ARG, "table_upload: bad argument");
+  cudaSetDevice(e->cfg.device);
+  const size_t need = e->tables_used + (size_t)((size + 31) & ~31);   /* 128-byte aligned starts */
+  if (need > e->tables_cap) {
+    size_t ncap = std::max(need, e->tables_cap * 2);
+    float *nt = nullptr;
+    CK(cudaMalloc((void **)&nt, ncap * sizeof(float)));
+    CK(cudaStreamSynchronize(e->last_stream ? e->last_stream : e->stream));
+    CK(cudaMemcpy(nt, e->d_tables, e->tables_used * sizeof(float), cudaMemcpyDeviceToDevice));
+    cudaFree(e->d_tables);
+    e->d_tables = nt;
+    e->tables_cap = ncap;
+  }
+  /* synchronous copy from pageable memory: table loads are cold (wire.c:406-441) */
+  CK(cudaMemcpy(e->d_tables + e->tables_used, data, (size_t)size * sizeof(float), cudaMemcpyHostToDevice));
+  TableDesc t = {e->tables_used, size};
+  e->tables.push_back(t);
+  e->tables_used = need;
+  return (int)e->tables.size() - 1;
+}
+
+int skb_set_params(skb_engine *e, int voice, const skb_voice_params *p) {
+  if (!e || !p || voice < 0 || voice >= e->n) return fail(e, SKB_ERR_ARG, "set_params: bad voice");
+  e->par[voice] = *p;
+  if (!e->dirty[voice]) { e->dirty[voice] = 1; e->dirty_list.push_back(voice); }
+  e->stats.params_uploaded++;
+  return SKB_OK;
+}
+
+int skb_push_ops(skb_engine *e, const skb_op *ops, int n) {
+  if (!e || n < 0 || (n > 0 && !ops)) return fail(e, SKB_ERR_ARG, "push_ops: bad argument");
+  e->ops.insert(e->ops.end(), ops, ops + n);
+  return SKB_OK;
+}
+
+/* ---- planner ------------------------------------------------------------ */
+static uint64_t edge_signature(const skb_voice_params *p, int v, int n) {
+  int m[4];
+  skb_live_mods(p, v, n, m);
+  uint64_t h = 1469598103934665603ull;
+  for (int k = 0; k < 4; k++) {
+    int x = (m[k] == v) ? -2 : m[k];          /* self reads are not edges */
+    h = (h ^ (uint64_t)(uint32_t)x) * 1099511628211ull;
+  }
+  return h;
+}
+
+/* Sort key of a free voice: voices that take the same branches share warps. */
+static uint64_t feature_key(const skb_voice_params *p) {
+  uint64_t k = 0;
+  const bool silent = (p->amp == 0.0f);
+  k |= (uint64_t)(silent ? 1 : 0) << 40;
+  k |= (uint64_t)((p->flags & SKB_F_NOISE) ? 1 : 0) << 39;
+  k |= (uint64_t)(p->cz_mode & 7) << 36;
+  k |= (uint64_t)(p->filter_mode ? 1 : 0) << 35;
+  k |= (uint64_t)((p->flags & SKB_F_USE_ENV) ? 1 : 0) << 34;
+  k |= (uint64_t)(p->quantize ? 1 : 0) << 33;
+  k |= (uint64_t)(p->sample_hold_max ? 1 : 0) << 32;
+  k |= (uint64_t)((p->flags & SKB_F_ONE_SHOT) ? 1 : 0) << 31;
+  k |= (uint64_t)((uint32_t)(p->table_id + 1) & 0x7fffffffu);
+  return k;
+}
+
+/* Translate a modulator voice index into the device reference of `v`. */
+static int make_ref(const skb_engine *e, int v, int m, bool none_if_negative) {
+  if (m < 0) return none_if_negative ? SKB_REF_NONE : SKB_REF_ZERO;
+  if (m >= e->n) return SKB_REF_ZERO;
+  if (m == v) return SKB_REF_SELF;
+  const int b = e->bin_of_voice[v];
+  if (b < 0 || e->bin_of_voice[m] != b) return SKB_REF_ZERO;   /* cannot happen for a live edge */
+  const int l = e->slot_of_voice[m] - e->bins[b].slot0;
+  return l | (m < v ? SKB_REF_CUR : 0);
+}
+
+static void pack_record(const skb_engine *e, int v, float4 *r) {
+  const skb_voice_params &p = e->par[v];
+  int live[4];
+  skb_live_mods(&p, v, e->n, live);
+  const bool noise = (p.flags & SKB_F_NOISE) != 0;
+  /* FM: only a live edge modulates (mod != n, synth.c:549) */
+  const int fm_ref = (live[0] >= 0) ? make_ref(e, v, live[0], true) : SKB_REF_NONE;
+  /* CZ: negative osc -> the literal 1.0f (synth.c:264); depth 0 / out of range -> 0.0f */
+  int cz_ref;
+  if (p.cz_mod_osc < 0) cz_ref = SKB_REF_NONE;
+  else if (p.cz_mod_osc == v) cz_ref = SKB_REF_SELF;
+  else if (live[1] >= 0) cz_ref = make_ref(e, v, live[1], true);
+  else cz_ref = SKB_REF_ZERO;
+  const int am_ref = make_ref(e, v, p.amp_mod_osc, true);
+  int pm_ref = make_ref(e, v, p.pan_mod_osc, true);
+  if (p.flags & SKB_F_DISCONNECT) pm_ref = SKB_REF_NONE;        /* never evaluated, synth.c:595 */
+  int toff = -1, tsize = p.table_size;
+  if (!noise && p.table_id >= 0 && p.table_id < (int)e->tables.size()) {
+    toff = (int)e->tables[p.table_id].off;
+    if (tsize > e->tables[p.table_id].size) tsize = e->tables[p.table_id].size;   /* never read past the upload */
+  }
+  auto fi = [](int x) { float f; memcpy(&f, &x, 4); return f; };
+  auto fu = [](uint32_t x) { float f; memcpy(&f, &x, 4); return f; };
+  r[0] = make_float4(p.amp, p.phase_inc, p.freq_scale, p.freq_mod_depth);
+  r[1] = make_float4(fi(fm_ref), fi(toff), fi(tsize), fu(p.flags));
+  r[2] = make_float4(p.loop_start_f, p.loop_end_f, p.cz_distortion, p.cz_mod_depth);
+  r[3] = make_float4(fi(p.cz_mode), fi(cz_ref), fi(p.sample_hold_max), fi(p.quantize));
+  r[4] = make_float4(p.b0, p.b1, p.b2, p.a1);
+  r[5] = make_float4(p.a2, p.env_attack, p.env_decay, p.env_sustain);
+  r[6] = make_float4(p.env_release, p.amp_mod_depth, p.smoother_k, p.pan_mod_depth);
+  r[7] = make_float4(fi(p.filter_mode), fi(am_ref), fi(pm_ref), fi(e->level[v]));
+}
+
+static int wait_staging(skb_engine *e) {
+  CK(cudaEventSynchronize(e->ev_h2d));
+  return SKB_OK;
+}
+
+static int replan(skb_engine *e, cudaStream_t st) {
+  const int n = e->n, rank = e->cfg.rank, world = e->cfg.world;
+  std::vector<int32_t> old_owner;
+  if (e->planned && world > 1) old_owner = e->owner;
+  skb_components(e->par.data(), n, e->comp.data());
+  skb_partition(e->comp.data(), n, world, e->owner.data());
+  if (e->planned && world > 1 && e->stats.frames_rendered > 0) {
+    for (int v = 0; v < n; v++)
+      if (old_owner[v] != e->owner[v])
+        return fail(e, SKB_ERR_STATE, "re-plan moved a voice to another shard: migrate its state with skb_snapshot/skb_restore");
+  }
+  std::vector<int32_t> csize(n, 0);
+  for (int v = 0; v < n; v++) csize[e->comp[v]]++;
+  /* free voices */
+  std::vector<std::pair<uint64_t, int32_t>> fr;
+  std::vector<int32_t> roots;
+  for (int v = 0; v < n; v++) {
+    if (e->owner[v] != rank) continue;
+    if (csize[e->comp[v]] == 1) fr.push_back(std::make_pair(feature_key(&e->par[v]), v));
+    else if (e->comp[v] == v) roots.push_back(v);
+  }
+  std::sort(fr.begin(), fr.end());
+  const std::vector<int32_t> old_slot_of_voice = e->slot_of_voice;
+  std::fill(e->slot_of_voice.begin(), e->slot_of_voice.end(), -1);
+  std::fill(e->bin_of_voice.begin(), e->bin_of_voice.end(), -1);
+  std::fill(e->level.begin(), e->level.end(), 0);
+  e->voice_of_slot.assign(e->cap, -1);
+  e->n_free = (int)fr.size();
+  e->n_free_pad = (e->n_free + 31) & ~31;
+  for (int i = 0; i < e->n_free; i++) {
+    e->slot_of_voice[fr[i].second] = i;
+    e->voice_of_slot[i] = fr[i].second;
+  }
+  /* bins: components in order of their smallest voice, first-fit in order */
+  std::vector<std::vector<int32_t>> members(roots.size());
+  {
+    std::vector<int32_t> ridx(n, -1);
+    for (size_t i = 0; i < roots.size(); i++) ridx[roots[i]] = (int32_t)i;
+    for (int v = 0; v < n; v++)
+      if (e->owner[v] == rank && csize[e->comp[v]] > 1) members[ridx[e->comp[v]]].push_back(v);
+  }
+  e->bins.clear();
+  std::vector<std::vector<int32_t>> binv;
+  for (size_t i = 0; i < roots.size(); i++) {
+    const int sz = (int)members[i].size();
+    if (sz > SKB_BIN_MAX)
+      return fail(e, SKB_ERR_CAPACITY, "a modulation group has more than 1024 voices");
+    if (binv.empty() || (int)binv.back().size() + sz > SKB_BIN_PACK) binv.push_back(std::vector<int32_t>());
+    binv.back().insert(binv.back().end(), members[i].begin(), members[i].end());
+  }
+  int slot = e->n_free_pad;
+  e->n_free_rows = e->n_free_pad / 32;
+  e->max_bin_threads = 0;
+  for (size_t b = 0; b < binv.size(); b++) {
+    std::sort(binv[b].begin(), binv[b].end());
+    skb_bin_desc d;
+    d.slot0 = slot; d.size = (int)binv[b].size(); d.nlevels = 1; d.row = e->n_free_rows + (int)b;
+    for (int i = 0; i < d.size; i++) {
+      const int v = binv[b][i];
+      e->slot_of_voice[v] = slot + i;
+      e->voice_of_slot[slot + i] = v;
+      e->bin_of_voice[v] = (int)b;
+      int live[4], lv = 0;
+      skb_live_mods(&e->par[v], v, n, live);
+      for (int k = 0; k < 4; k++)
+        if (live[k] >= 0 && live[k] < v) lv = std::max(lv, e->level[live[k]] + 1);
+      e->level[v] = lv;
+      d.nlevels = std::max(d.nlevels, lv + 1);
+    }
+    e->bins.push_back(d);
+    e->max_bin_threads = std::max(e->max_bin_threads, (d.size + 31) & ~31);
+    slot += d.size;
+  }
+  e->n_slots = slot;
+  e->n_rows = e->n_free_rows + (int)e->bins.size();
+  if (e->n_slots > e->cap) return fail(e, SKB_ERR_CAPACITY, "slot capacity exceeded");
+  for (int v = 0; v < n; v++) e->edge_sig[v] = edge_signature(&e->par[v], v, n);
+
+  cudaError_t r;
+  /* carry evolving state over to the new slots */
+  if (wait_staging(e)) return e->err;
+  if ((r = grow_pin(&e->h_idx, &e->h_idx_cap, (size_t)e->cap)) != cudaSuccess ||
+      (r = grow_dev(&e->d_idx, &e->d_idx_cap, (size_t)e->cap)) != cudaSuccess)
+    return fail(e, SKB_ERR_CUDA, "replan alloc", cudaGetErrorString(r));
+  for (int s = 0; s < e->cap; s++) {
+    const int v = e->voice_of_slot[s];
+    e->h_idx[s] = (v >= 0) ? old_slot_of_voice[v] : -1;
+  }
+  CK(cudaMemcpyAsync(e->d_idx, e->h_idx, (size_t)e->cap * sizeof(int), cudaMemcpyHostToDevice, st));
+  {
+    const int total = e->cap * SKB_NSQ;
+    k_permute_state<<<(total + 255) / 256, 256, 0, st>>>(e->d_sq[e->cur], e->d_sq[e->cur ^ 1], e->cap, e->d_idx, e->cap);
+    e->stats.kernel_launches++;
+    e->cur ^= 1;
+  }
+  CK(cudaMemsetAsync(e->d_pq, 0, (size_t)SKB_NPQ * e->cap * sizeof(float4), st));
+  CK(cudaEventRecord(e->ev_h2d, st));
+  if (!e->bins.empty()) {
+    if ((int)e->bins.size() > e->d_bins_cap) {
+      cudaFree(e->d_bins);
+      e->d_bins_cap = (int)e->bins.size() * 2;
+      CK(cudaMalloc((void **)&e->d_bins, (size_t)e->d_bins_cap * sizeof(skb_bin_desc)));
+    }
+    /* pageable source: synchronous with respect to the host, ordered on st */
+    CK(cudaMemcpyAsync(e->d_bins, e->bins.data(), e->bins.size() * sizeof(skb_bin_desc), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  /* every owned voice gets a fresh record */
+  std::fill(e->noise_flag.begin(), e->noise_flag.end(), 0);
+  e->noise_count = 0;
+  for (size_t i = 0; i < e->dirty_list.size(); i++) e->dirty[e->dirty_list[i]] = 0;
+  e->dirty_list.clear();
+  for (int v = 0; v < n; v++)
+    if (e->slot_of_voice[v] >= 0) { e->dirty[v] = 1; e->dirty_list.push_back(v); }
+  e->planned = true;
+  e->need_plan = false;
+  e->stats.replans++;
+  e->stats.n_free_voices = e->n_free;
+  e->stats.n_group_voices = e->n_slots - e->n_free_pad;
+  e->stats.n_groups = (int)e->bins.size();
+  e->stats.n_owned_voices = e->n_free + e->stats.n_group_voices;
+  return SKB_OK;
+}
+
+/* Work is ordered by stream; when the caller switches streams (its own NCCL
+ * stream vs the engine's), drain the previous one first. */
+static int use_stream(skb_engine *e, cudaStream_t st) {
+  if (e->last_stream && e->last_stream != st) CK(cudaStreamSynchronize(e->last_stream));
+  e->last_stream = st;
+  return SKB_OK;
+}
+
+/* Bring the device up to date with everything the host sent: plan, parameter
+ * records, ordered ops. */
+static int sync_inputs(skb_engine *e, cudaStream_t st) {
+  if (e->err) return e->err;
+  if (!e->planned) e->need_plan = true;
+  if (!e->need_plan)
+    for (size_t i = 0; i < e->dirty_list.size(); i++) {
+      const int v = e->dirty_list[i];
+      if (edge_signature(&e->par[v], v, e->n) != e->edge_sig[v]) { e->need_plan = true; break; }
+    }
+  if (e->need_plan && replan(e, st)) return e->err;
+  cudaError_t r;
+  if (!e->dirty_list.empty()) {
+    size_t cnt = 0;
+    for (size_t i = 0; i < e->dirty_list.size(); i++) cnt += e->slot_of_voice[e->dirty_list[i]] >= 0;
+    if (wait_staging(e)) return e->err;
+    if ((r = grow_pin(&e->h_idx, &e->h_idx_cap, cnt)) != cudaSuccess ||
+        (r = grow_dev(&e->d_idx, &e->d_idx_cap, cnt)) != cudaSuccess ||
+        (r = grow_pin(&e->h_recs, &e->h_recs_cap, cnt * SKB_NPQ)) != cudaSuccess ||
+        (r = grow_dev(&e->d_recs, &e->d_recs_cap, cnt * SKB_NPQ)) != cudaSuccess)
+      return fail(e, SKB_ERR_CUDA, "param staging alloc", cudaGetErrorString(r));
+    size_t j = 0;
+    for (size_t i = 0; i < e->dirty_list.size(); i++) {
+      const int v = e->dirty_list[i];
+      e->dirty[v] = 0;
+      if (e->slot_of_voice[v] < 0) continue;
+      e->h_idx[j] = e->slot_of_voice[v];
+      pack_record(e, v, e->h_recs + j * SKB_NPQ);
+      const uint8_t nz = (e->par[v].flags & SKB_F_NOISE) ? 1 : 0;
+      e->noise_count += (int)nz - (int)e->noise_flag[v];
+      e->noise_flag[v] = nz;
+      j++;
+    }
+    e->dirty_list.clear();
+    if (cnt) {
+      CK(cudaMemcpyAsync(e->d_idx, e->h_idx, cnt * sizeof(int), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(e->d_recs, e->h_recs, cnt * SKB_NPQ * sizeof(float4), cudaMemcpyHostToDevice, st));
+      const int total = (int)cnt * SKB_NPQ;
+      k_scatter_params<<<(total + 255) / 256, 256, 0, st>>>(e->d_pq, e->cap, e->d_idx, e->d_recs, (int)cnt);
+      e->stats.kernel_launches++;
+      CK(cudaEventRecord(e->ev_h2d, st));
+    }
+    e->any_noise = e->noise_count > 0;
+  }
+  if (!e->ops.empty()) {
+    /* keep per-voice order: stable sort by slot, then one run per slot */
+    std::vector<skb_op> &ops = e->ops;
+    size_t cnt = 0;
+    for (size_t i = 0; i < ops.size(); i++) {
+      const int v = ops[i].voice;
+      if (v < 0 || v >= e->n || e->slot_of_voice[v] < 0) continue;
+      ops[cnt] = ops[i];
+      ops[cnt].voice = e->slot_of_voice[v];
+      cnt++;
+    }
+    e->stats.ops_applied += ops.size();
+    ops.resize(cnt);
+    if (cnt) {
+      std::stable_sort(ops.begin(), ops.end(), [](const skb_op &a, const skb_op &b) { return a.voice < b.voice; });
+      if (wait_staging(e)) return e->err;
+      if ((r = grow_pin(&e->h_ops, &e->h_ops_cap, cnt)) != cudaSuccess ||
+          (r = grow_pin(&e->h_runs, &e->h_runs_cap, cnt)) != cudaSuccess ||
+          (r = grow_dev(&e->d_ops, &e->d_ops_cap, cnt)) != cudaSuccess ||
+          (r = grow_dev(&e->d_runs, &e->d_runs_cap, cnt)) != cudaSuccess)
+        return fail(e, SKB_ERR_CUDA, "op staging alloc", cudaGetErrorString(r));
+      memcpy(e->h_ops, ops.data(), cnt * sizeof(skb_op));
+      int nruns = 0;
+      for (size_t i = 0; i < cnt;) {
+        size_t j = i + 1;
+        while (j < cnt && ops[j].voice == ops[i].voice) j++;
+        e->h_runs[nruns++] = make_int2((int)i, (int)j);
+        i = j;
+      }
+      CK(cudaMemcpyAsync(e->d_ops, e->h_ops, cnt * sizeof(skb_op), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(e->d_runs, e->h_runs, (size_t)nruns * sizeof(int2), cudaMemcpyHostToDevice, st));
+      k_apply_ops<<<(nruns + 127) / 128, 128, 0, st>>>(e->d_sq[e->cur], e->cap, e->d_ops, e->d_runs, nruns);
+      e->stats.kernel_launches++;
+      CK(cudaEventRecord(e->ev_h2d, st));
+    }
+    ops.clear();
+  }
+  return SKB_OK;
+}
+
+int skb_owns_voice(skb_engine *e, int voice) {
+  if (!e || voice < 0 || voice >= e->n) return 0;
+  if (e->cfg.world == 1) return 1;
+  cudaSetDevice(e->cfg.device);
+  if (use_stream(e, e->stream) || sync_inputs(e, e->stream)) return 0;
+  return e->owner[voice] == e->cfg.rank;
+}
+
+int skb_render_mix(skb_engine *e, int nframes, uint64_t ssc_before, const float *noise,
+                   float *d_mix, void *stream) {
+  if (!e) return SKB_ERR_ARG;
+  if (nframes < 0 || nframes > e->cfg.max_frames || !d_mix) return fail(e, SKB_ERR_ARG, "render_mix: bad argument");
+  cudaSetDevice(e->cfg.device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  if (use_stream(e, st)) return e->err;
+  if (sync_inputs(e, st)) return e->err;
+  if (nframes == 0) return e->err;
+  if (e->any_noise) {
+    if (!noise) return fail(e, SKB_ERR_ARG, "render_mix: a voice uses the shared noise source but noise == NULL");
+    if (wait_staging(e)) return e->err;
+    memcpy(e->h_noise, noise, (size_t)nframes * sizeof(float));
+    CK(cudaMemcpyAsync(e->d_noise, e->h_noise, (size_t)nframes * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(e->ev_h2d, st));
+  }
+  const size_t need = (size_t)std::max(e->n_rows, 1) * (size_t)nframes;
+  if (need > e->partials_cap) {
+    CK(cudaStreamSynchronize(st));
+    cudaError_t r = grow_dev(&e->d_partials, &e->partials_cap, (size_t)std::max(e->n_rows, 1) * (size_t)e->cfg.max_frames);
+    if (r != cudaSuccess) return fail(e, SKB_ERR_CUDA, "partials alloc", cudaGetErrorString(r));
+  }
+  CK(cudaEventRecord(e->ev_t0, st));
+  if (e->n_free_pad > 0) {
+    const int grid = (e->n_free_pad + SKB_FREE_THREADS - 1) / SKB_FREE_THREADS;
+    k_render_free<<<grid, SKB_FREE_THREADS, 0, st>>>(e->d_pq, e->d_sq[e->cur], e->cap, e->n_free_pad, e->d_tables,
+                                                     e->d_noise, nframes, (unsigned long long)ssc_before,
+                                                     e->d_partials, nframes);
+    e->stats.kernel_launches++;
+  }
+  if (!e->bins.empty()) {
+    const int nt = e->max_bin_threads;
+    const size_t smem = (size_t)3 * nt * sizeof(float) + (size_t)2 * (nt / 32) * sizeof(float2);
+    k_render_bins<<<(int)e->bins.size(), nt, smem, st>>>(e->d_pq, e->d_sq[e->cur], e->cap, e->d_bins, e->d_tables,
+                                                         e->d_noise, nframes, (unsigned long long)ssc_before,
+                                                         e->d_partials, nframes);
+    e->stats.kernel_launches++;
+  }
+  if (e->n_rows > 0) {
+    dim3 blk(SKB_RED_X, SKB_RED_Y);
+    k_reduce_rows<<<(nframes + SKB_RED_X - 1) / SKB_RED_X, blk, 0, st>>>(e->d_partials, e->n_rows, nframes, nframes,
+                                                                           (float2 *)d_mix);
+    e->stats.kernel_launches++;
+  } else {
+    CK(cudaMemsetAsync(d_mix, 0, (size_t)nframes * sizeof(float2), st));
+  }
+  CK(cudaEventRecord(e->ev_t1, st));
+  e->timing_pending = true;
+  CK(cudaGetLastError());
+  e->stats.frames_rendered += (uint64_t)nframes;
+  return e->err;
+}
+
+int skb_finish(skb_engine *e, const float *d_mix, int nframes, const float *gain, float *out,
+               int num_channels, void *stream) {
+  if (!e) return SKB_ERR_ARG;
+  if (!d_mix || !gain || !out || num_channels < 2 || nframes < 0 || nframes > e->cfg.max_frames)
+    return fail(e, SKB_ERR_ARG, "finish: bad argument");
+  if (nframes == 0) return e->err;
+  cudaSetDevice(e->cfg.device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  if (use_stream(e, st)) return e->err;
+  if (wait_staging(e)) return e->err;
+  memcpy(e->h_gain, gain, (size_t)nframes * sizeof(float));
+  CK(cudaMemcpyAsync(e->d_gain, e->h_gain, (size_t)nframes * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(e->ev_h2d, st));
+  k_finish<<<(nframes + 255) / 256, 256, 0, st>>>((const float2 *)d_mix, e->d_gain, e->d_out, nframes);
+  e->stats.kernel_launches++;
+  CK(cudaMemcpyAsync(e->h_out, e->d_out, (size_t)nframes * sizeof(float2), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (num_channels == 2) {
+    memcpy(out, e->h_out, (size_t)nframes * sizeof(float2));
+  } else {
+    const float *h = e->h_out;
+    for (int i = 0; i < nframes; i++) {           /* only channels 0 and 1 are written, synth.c:623-624 */
+      out[(size_t)i * num_channels + 0] = h[2 * i + 0];
+      out[(size_t)i * num_channels + 1] = h[2 * i + 1];
+    }
+  }
+  if (e->timing_pending) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1) == cudaSuccess) e->stats.last_render_ms = ms;
+    else cudaGetLastError();
+    e->timing_pending = false;
+  }
+  return e->err;
+}
+
+int skb_render(skb_engine *e, int nframes, uint64_t ssc_before, const float *gain, const float *noise,
+               float *out, int num_channels) {
+  if (!e) return SKB_ERR_ARG;
+  if (nframes < 0 || !gain || !out) return fail(e, SKB_ERR_ARG, "render: bad argument");
+  int done = 0;
+  while (done < nframes) {
+    const int n = std::min(nframes - done, e->cfg.max_frames);
+    int r = skb_render_mix(e, n, ssc_before + (uint64_t)done, noise ? noise + done : nullptr, (float *)e->d_mix, nullptr);
+    if (r) return r;
+    r = skb_finish(e, (const float *)e->d_mix, n, gain + done, out + (size_t)done * num_channels, num_channels, nullptr);
+    if (r) return r;
+    done += n;
+  }
+  return e->err;
+}
+
+int skb_sync(skb_engine *e, void *stream) {
+  if (!e) return SKB_ERR_ARG;
+  cudaSetDevice(e->cfg.device);
+  CK(cudaStreamSynchronize(stream ? (cudaStream_t)stream : e->stream));
+  if (e->timing_pending) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1) == cudaSuccess) e->stats.last_render_ms = ms;
+    else cudaGetLastError();
+    e->timing_pending = false;
+  }
+  return e->err;
+}
+
+static int stage_slots(skb_engine *e, int first, int n) {
+  cudaError_t r;
+  if (wait_staging(e)) return e->err;
+  if ((r = grow_pin(&e->h_idx, &e->h_idx_cap, (size_t)n)) != cudaSuccess ||
+      (r = grow_dev(&e->d_idx, &e->d_idx_cap, (size_t)n)) != cudaSuccess ||
+      (r = grow_pin(&e->h_snap, &e->h_snap_cap, (size_t)n)) != cudaSuccess ||
+      (r = grow_dev(&e->d_snap, &e->d_snap_cap, (size_t)n)) != cudaSuccess)
+    return fail(e, SKB_ERR_CUDA, "snapshot alloc", cudaGetErrorString(r));
+  for (int i = 0; i < n; i++) e->h_idx[i] = e->slot_of_voice[first + i];
+  return SKB_OK;
+}
+
+int skb_snapshot(skb_engine *e, int first, int n, skb_voice_state *out) {
+  if (!e || first < 0 || n < 0 || first + n > e->n || !out) return fail(e, SKB_ERR_ARG, "snapshot: bad range");
+  if (n == 0) return e->err;
+  cudaSetDevice(e->cfg.device);
+  cudaStream_t st = e->stream;
+  if (use_stream(e, st)) return e->err;
+  if (sync_inputs(e, st)) return e->err;
+  if (stage_slots(e, first, n)) return e->err;
+  CK(cudaMemcpyAsync(e->d_idx, e->h_idx, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+  k_gather_state<<<(n + 127) / 128, 128, 0, st>>>(e->d_sq[e->cur], e->cap, e->d_idx, n, e->d_snap);
+  e->stats.kernel_launches++;
+  CK(cudaMemcpyAsync(e->h_snap, e->d_snap, (size_t)n * sizeof(skb_voice_state), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  memcpy(out, e->h_snap, (size_t)n * sizeof(skb_voice_state));
+  return e->err;
+}
+
+int skb_restore(skb_engine *e, int first, int n, const skb_voice_state *in) {
+  if (!e || first < 0 || n < 0 || first + n > e->n || !in) return fail(e, SKB_ERR_ARG, "restore: bad range");
+  if (n == 0) return e->err;
+  cudaSetDevice(e->cfg.device);
+  cudaStream_t st = e->stream;
+  if (use_stream(e, st)) return e->err;
+  if (sync_inputs(e, st)) return e->err;
+  if (stage_slots(e, first, n)) return e->err;
+  memcpy(e->h_snap, in, (size_t)n * sizeof(skb_voice_state));
+  CK(cudaMemcpyAsync(e->d_idx, e->h_idx, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(e->d_snap, e->h_snap, (size_t)n * sizeof(skb_voice_state), cudaMemcpyHostToDevice, st));
+  k_scatter_state<<<(n + 127) / 128, 128, 0, st>>>(e->d_sq[e->cur], e->cap, e->d_idx, n, e->d_snap);
+  e->stats.kernel_launches++;
+  CK(cudaStreamSynchronize(st));
+  return e->err;
+}
+
+int skb_get_stats(skb_engine *e, skb_stats *out) {
+  if (!e || !out) return SKB_ERR_ARG;
+  *out = e->stats;
+  return SKB_OK;
+}

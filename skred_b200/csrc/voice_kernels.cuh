@@ -1,0 +1,557 @@
+/* voice_kernels.cuh — sm_100a device code of the voice-render path.
+ *
+ * Replaces the frame-outer / voice-inner loop of synth() (synth.c:520-613).
+ * Exactness contract: this TU is compiled with
+ *   -fmad=false -prec-div=true -prec-sqrt=true -ftz=false
+ * so every float op below is ONE individually rounded IEEE-754 binary32 op in
+ * the reference's evaluation order — the same thing `gcc -O2
+ * -ffp-contract=off` emits for synth.c on x86-64/SSE2.  The phase
+ * recurrence, table index and `finished` latch are therefore bit-identical
+ * to the reference; only the ORDER OF THE CROSS-VOICE SUM differs (fixed,
+ * documented in DESIGN.md), which is inside the 1e-5 float budget.
+ *
+ * Layout.  Parameters and evolving state live in HBM as float4-packed
+ * structure-of-arrays indexed by SLOT (q[k][slot]); a warp's 32 threads read
+ * 32 consecutive float4 = 512 contiguous bytes per field group.  Slots are a
+ * permutation of voices chosen by the host planner (engine.cu): free voices
+ * first, sorted so that a warp is homogeneous in CZ mode / filter / table,
+ * then modulation groups.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math_constants.h>
+#include "skred_b200.h"
+
+#define SKB_NPQ 8          /* float4 groups per voice: parameters (32 words) */
+#define SKB_NSQ 5          /* float4 groups per voice: evolving state (18 of 20 words) */
+#define SKB_FREE_THREADS 64
+#define SKB_CHUNK 32       /* frames per warp-level transpose-reduce */
+#define SKB_REF_NONE (-1)      /* no modulator: the reference's literal for that site (1.0f / no FM) */
+#define SKB_REF_SELF (-2)      /* the voice reads its own voice_sample */
+#define SKB_REF_ZERO (-3)      /* modulator contributes an identical 0.0f (depth-0 CZ default, out-of-range osc) */
+#define SKB_REF_CUR  (1 << 20)   /* read the modulator's CURRENT-frame value (m < n) */
+#define SKB_REF_MASK ((1 << 20) - 1)
+
+struct VoiceP {
+  float amp, inc, fscale, fm_depth;
+  int fm_ref, toff, tsize; unsigned flags;
+  float lo, hi, cz_dist, cz_depth;
+  int cz_mode, cz_ref, sh_max, quant;
+  float b0, b1, b2, a1;
+  float a2, envA, envD, envS;
+  float envR, am_depth, sm_k, pm_depth;
+  int fmode, am_ref, pm_ref, level;
+};
+
+struct VoiceS {
+  float phase; int finished; float sample, sh_hold;
+  int sh_count; float x1, x2, y1;
+  float y2; int env_active; float env_vel, sm_gain;
+  float panL, panR; unsigned long long env_start;
+  unsigned long long env_rel;
+};
+
+__device__ __forceinline__ float4 ldq(const float4 *base, int k, int cap, int slot) {
+  return base[(size_t)k * cap + slot];
+}
+
+__device__ __forceinline__ void load_params(const float4 *__restrict__ q, int cap, int slot, VoiceP &p) {
+  float4 a;
+  a = ldq(q, 0, cap, slot); p.amp = a.x; p.inc = a.y; p.fscale = a.z; p.fm_depth = a.w;
+  a = ldq(q, 1, cap, slot); p.fm_ref = __float_as_int(a.x); p.toff = __float_as_int(a.y); p.tsize = __float_as_int(a.z); p.flags = __float_as_uint(a.w);
+  a = ldq(q, 2, cap, slot); p.lo = a.x; p.hi = a.y; p.cz_dist = a.z; p.cz_depth = a.w;
+  a = ldq(q, 3, cap, slot); p.cz_mode = __float_as_int(a.x); p.cz_ref = __float_as_int(a.y); p.sh_max = __float_as_int(a.z); p.quant = __float_as_int(a.w);
+  a = ldq(q, 4, cap, slot); p.b0 = a.x; p.b1 = a.y; p.b2 = a.z; p.a1 = a.w;
+  a = ldq(q, 5, cap, slot); p.a2 = a.x; p.envA = a.y; p.envD = a.z; p.envS = a.w;
+  a = ldq(q, 6, cap, slot); p.envR = a.x; p.am_depth = a.y; p.sm_k = a.z; p.pm_depth = a.w;
+  a = ldq(q, 7, cap, slot); p.fmode = __float_as_int(a.x); p.am_ref = __float_as_int(a.y); p.pm_ref = __float_as_int(a.z); p.level = __float_as_int(a.w);
+}
+
+__device__ __forceinline__ void load_state(const float4 *__restrict__ q, int cap, int slot, VoiceS &s) {
+  float4 a;
+  a = ldq(q, 0, cap, slot); s.phase = a.x; s.finished = __float_as_int(a.y); s.sample = a.z; s.sh_hold = a.w;
+  a = ldq(q, 1, cap, slot); s.sh_count = __float_as_int(a.x); s.x1 = a.y; s.x2 = a.z; s.y1 = a.w;
+  a = ldq(q, 2, cap, slot); s.y2 = a.x; s.env_active = __float_as_int(a.y); s.env_vel = a.z; s.sm_gain = a.w;
+  a = ldq(q, 3, cap, slot); s.panL = a.x; s.panR = a.y;
+  s.env_start = ((unsigned long long)__float_as_uint(a.w) << 32) | __float_as_uint(a.z);
+  a = ldq(q, 4, cap, slot);
+  s.env_rel = ((unsigned long long)__float_as_uint(a.y) << 32) | __float_as_uint(a.x);
+}
+
+__device__ __forceinline__ void store_state(float4 *__restrict__ q, int cap, int slot, const VoiceS &s) {
+  q[(size_t)0 * cap + slot] = make_float4(s.phase, __int_as_float(s.finished), s.sample, s.sh_hold);
+  q[(size_t)1 * cap + slot] = make_float4(__int_as_float(s.sh_count), s.x1, s.x2, s.y1);
+  q[(size_t)2 * cap + slot] = make_float4(s.y2, __int_as_float(s.env_active), s.env_vel, s.sm_gain);
+  q[(size_t)3 * cap + slot] = make_float4(s.panL, s.panR, __uint_as_float((unsigned)(s.env_start & 0xffffffffull)),
+                                          __uint_as_float((unsigned)(s.env_start >> 32)));
+  q[(size_t)4 * cap + slot] = make_float4(__uint_as_float((unsigned)(s.env_rel & 0xffffffffull)),
+                                          __uint_as_float((unsigned)(s.env_rel >> 32)), 0.0f, 0.0f);
+}
+
+/* C's (int)float on x86-64 is cvttss2si: anything unrepresentable (NaN, +-Inf,
+ * |v| >= 2^31) yields INT_MIN, whereas cvt.rzi.s32.f32 saturates and maps NaN
+ * to 0.  Needed where the reference can overflow: fast_pow (synth.c:145) and
+ * the CZ-warped index (synth.c:265). */
+__device__ __forceinline__ int c_f2i(float v) {
+  return (v < 2147483648.0f) ? __float2int_rz(v) : (int)0x80000000;
+}
+__device__ __forceinline__ int c_d2i(double v) {
+  return (v < 2147483648.0) ? __double2int_rz(v) : (int)0x80000000;
+}
+
+/* fast_pow, synth.c:140-147 */
+__device__ __forceinline__ float dev_fast_pow(float a, float b) {
+  if (a <= 0.0f) return 0.0f;
+  int ai = __float_as_int(a);
+  float t = b * __int2float_rn(ai - 1065353216);
+  t = t + 1065353216.0f;
+  return __int_as_float(c_f2i(t));
+}
+
+/* Per-block constants of one voice that the reference recomputes every sample
+ * from unchanged inputs (identical bits, fewer instructions). */
+struct VoiceK {
+  float lo, hi, span, span2;  /* wrap window, synth.c:235-239 */
+  float size_f, inv_size;     /* inv_size != 0 iff table_size is a power of two (x/2^k == x*2^-k exactly) */
+  bool stop_at_end;           /* one_shot && !loop_enabled, synth.c:243,250 */
+  int one_shot;
+};
+
+__device__ __forceinline__ void derive_consts(const VoiceP &p, VoiceK &k) {
+  const bool loop_on = (p.flags & SKB_F_LOOP_ENABLED) != 0;
+  const bool use_loop = loop_on && (p.flags & SKB_F_LOOP_VALID);
+  k.size_f = __int2float_rn(p.tsize);
+  k.lo = use_loop ? p.lo : 0.0f;
+  k.hi = use_loop ? p.hi : k.size_f;
+  k.span = k.hi - k.lo;
+  k.span2 = k.span + k.span;
+  k.one_shot = (p.flags & SKB_F_ONE_SHOT) ? 1 : 0;
+  k.stop_at_end = k.one_shot && !loop_on;
+  const bool pow2 = p.tsize > 0 && (p.tsize & (p.tsize - 1)) == 0;
+  k.inv_size = pow2 ? (1.0f / k.size_f) : 0.0f;
+}
+
+/* fmodf(x, y) for x >= 0, y > 0.  fmodf is exact by definition; when
+ * y <= x < 2y the result x - y is exact too (Sterbenz), so the common
+ * single-wrap case needs one subtraction. */
+__device__ __forceinline__ float wrap_mod(float x, float y, float y2) {
+  if (x < y) return x;
+  if (x < y2) return x - y;
+  return fmodf(x, y);
+}
+
+/* cz_phasor, synth.c:149-215.  `d` already includes the modulator term. */
+__device__ __forceinline__ float dev_cz_phasor(int mode, float ph_tab, float d, const VoiceK &k) {
+  float x = (k.inv_size != 0.0f) ? ph_tab * k.inv_size : ph_tab / k.size_f;     /* :151 */
+  d = (d < 0.0f) ? 0.0f : (d > 0.999f ? 0.999f : d);                              /* :154 */
+  switch (mode) {
+    case 1: {
+      if (x < d) x = x * (0.5f / d);
+      else x = 0.5f + (x - d) * (0.5f / (1.0f - d));
+      break;
+    }
+    case 2: {
+      const float sc = 0.5f / (0.5f - d * 0.5f);
+      x = (x < 0.5f) ? x * sc : 1.0f - (1.0f - x) * sc;
+      break;
+    }
+    case 3: {
+      const float sc = 0.5f / (0.5f - d * 0.5f);
+      x = (x < 0.5f) ? x * sc : 0.5f + (x - 0.5f) * sc;
+      break;
+    }
+    case 4: x = fmodf(x * 2.0f, 1.0f); break;
+    case 5: {
+      const float hd = d * 0.5f;
+      x = (x < 0.5f) ? x * (0.5f / (0.5f - hd)) : 0.5f + (x - 0.5f) * (0.5f / (0.5f + hd));
+      break;
+    }
+    case 6: x = dev_fast_pow(x, 1.0f + 4.0f * d); break;
+    case 7: x = dev_fast_pow(x, 1.0f + 8.0f * d); break;
+    default: return ph_tab;
+  }
+  return x * k.size_f;                                                            /* :214 */
+}
+
+/* amp_envelope_step, synth.c:398-431 */
+__device__ __forceinline__ float dev_env_step(const VoiceP &p, VoiceS &s, unsigned long long ssc) {
+  if (!s.env_active) return 0.0f;
+  const float t = __ull2float_rn(ssc - s.env_start);
+  if (t < p.envA) return t / p.envA;
+  if (t < p.envA + p.envD) {
+    const float prog = (t - p.envA) / p.envD;
+    return 1.0f - prog * (1.0f - p.envS);
+  }
+  if (s.env_rel == 0ull) return p.envS;
+  const float tr = __ull2float_rn(ssc - s.env_rel);
+  if (tr < p.envR) {
+    const float prog = tr / p.envR;
+    return p.envS * (1.0f - prog);
+  }
+  s.env_active = 0;
+  return 0.0f;
+}
+
+/* quantize_bits_int, synth.c:341-345 (double-precision +0.5, x86 shift-count masking) */
+__device__ __forceinline__ float dev_quantize(float v, int bits) {
+  const int levels = (1 << (bits & 31)) - 1;
+  const float lf = __int2float_rn(levels);
+  const int iv = c_d2i((double)(v * lf) + 0.5);
+  return __int2float_rn(iv) * (1.0f / lf);
+}
+
+/* Modulator access policy for voices without live cross-voice reads. */
+struct NoMods {
+  __device__ __forceinline__ float read(int) const { return 0.0f; }
+  __device__ __forceinline__ float inc_of(int) const { return 0.0f; }
+};
+
+template <bool MODS, class Mod>
+__device__ __forceinline__ float mod_value(int ref, float self_value, const Mod &mod) {
+  if (ref == SKB_REF_SELF) return self_value;
+  if (ref == SKB_REF_ZERO) return 0.0f;
+  return MODS ? mod.read(ref) : 0.0f;
+}
+
+/* One voice, one frame: the body of the `for n` loop, synth.c:526-612.
+ * Returns the voice's stereo contribution (0,0 when skipped/disconnected).
+ * `self_prev` semantics: a self-referencing CZ read sees last frame's final
+ * sample (synth.c:264 runs before :570), a self AM read sees the filtered
+ * sample (:586 after :577), a self pan read the final one (:599 after :593). */
+template <bool MODS, class Mod>
+__device__ __forceinline__ float2 voice_frame(const VoiceP &p, const VoiceK &k, VoiceS &s,
+                                              unsigned long long ssc, float white,
+                                              const float *__restrict__ tables, const Mod &mod) {
+  if (s.finished) { s.sample = 0.0f; return make_float2(0.0f, 0.0f); }          /* :531-536 */
+  if (p.amp == 0.0f) { s.sample = 0.0f; return make_float2(0.0f, 0.0f); }       /* :537-542 */
+  float f;
+  if (p.flags & SKB_F_NOISE) {                                                    /* :543-546 */
+    f = white;
+  } else {
+    float inc = p.inc;
+    if (MODS && p.fm_ref >= 0) {                                                  /* :548-555 (mod != n) */
+      const float g = mod.read(p.fm_ref) * p.fm_depth;
+      inc = p.inc + ((mod.inc_of(p.fm_ref) * p.fscale) * g);
+    }
+    /* osc_next, synth.c:217-275 */
+    if (p.flags & SKB_F_REVERSE) inc = -inc;                                      /* :224 */
+    float ph = s.phase + inc;                                                     /* :226 */
+    if (!(fabsf(ph) < CUDART_INF_F)) {                                            /* :228-232 !isfinite */
+      s.phase = 0.0f;
+      s.finished = k.one_shot;
+      f = 0.0f;
+    } else {
+      if (ph >= k.hi) {                                                           /* :242-248 */
+        if (k.stop_at_end) { ph = k.hi - 1e-6f; s.finished = 1; }
+        else ph = k.lo + wrap_mod(ph - k.lo, k.span, k.span2);
+      } else if (ph < k.lo) {                                                     /* :249-256 */
+        if (k.stop_at_end) { ph = k.lo; s.finished = 1; }
+        else ph = k.hi - wrap_mod(k.lo - ph, k.span, k.span2);
+      }
+      s.phase = ph;                                                               /* :258 */
+      int idx;
+      if (p.cz_mode) {                                                            /* :262-266 */
+        const float dm = (p.cz_ref == SKB_REF_NONE)
+                             ? 1.0f
+                             : mod_value<MODS>(p.cz_ref, s.sample, mod) * p.cz_depth;
+        idx = c_f2i(dev_cz_phasor(p.cz_mode, ph, p.cz_dist + dm, k));
+      } else {
+        idx = __float2int_rz(ph);                                                 /* :268 */
+      }
+      if (idx >= p.tsize) idx = p.tsize - 1;                                      /* :271-272 */
+      if (idx < 0) idx = 0;
+      f = (p.toff >= 0) ? __ldg(tables + p.toff + idx) : 0.0f;                    /* :274 */
+    }
+  }
+  float x;
+  if (p.sh_max) {                                                                 /* :560-571 */
+    if (s.sh_count == 0) s.sh_hold = f;
+    x = s.sh_hold;
+    s.sh_count++;
+    if (s.sh_count >= p.sh_max) s.sh_count = 0;
+  } else {
+    x = f;
+  }
+  if (p.quant) x = dev_quantize(x, p.quant);                                      /* :574 */
+  if (p.fmode) {                                                                  /* :577, :349-364 */
+    const float y = p.b0 * x + p.b1 * s.x1 + p.b2 * s.x2 - p.a1 * s.y1 - p.a2 * s.y2;
+    s.x2 = s.x1; s.x1 = x; s.y2 = s.y1; s.y1 = y;
+    x = y;
+  }
+  float env = 1.0f;                                                               /* :581-582 */
+  if (p.flags & SKB_F_USE_ENV) env = dev_env_step(p, s, ssc) * s.env_vel;
+  float am = 1.0f;                                                                /* :583-587 */
+  if (p.am_ref != SKB_REF_NONE) am = mod_value<MODS>(p.am_ref, x, mod) * p.am_depth;
+  float gain = p.amp * env * am;                                                  /* :588 */
+  if (p.flags & SKB_F_SMOOTHER) {                                                 /* :589-592 */
+    s.sm_gain = s.sm_gain + p.sm_k * (gain - s.sm_gain);
+    gain = s.sm_gain;
+  }
+  const float out = x * gain;                                                     /* :593 */
+  s.sample = out;
+  if (p.flags & SKB_F_DISCONNECT) return make_float2(0.0f, 0.0f);                 /* :595,609-612 */
+  if (p.pm_ref != SKB_REF_NONE) {                                                 /* :597-602 */
+    const float q = mod_value<MODS>(p.pm_ref, out, mod) * p.pm_depth;
+    s.panL = (1.0f - q) / 2.0f;
+    s.panR = (1.0f + q) / 2.0f;
+  }
+  return make_float2(out * s.panL, out * s.panR);                                 /* :603-604 */
+}
+
+/* ======================================================================== */
+/* K1  render_free: voices with no live cross-voice reads                    */
+/* ======================================================================== */
+/* 1 thread = 1 voice (slot), looping the frames with every evolving word in
+ * registers.  Stereo contributions go through a per-warp shared-memory tile
+ * [SKB_CHUNK frames][32 lanes] that is read back TRANSPOSED: lane f adds the 32
+ * voices of frame f in lane order (fixed order => run-to-run deterministic) and
+ * stores one coalesced 256-byte row segment of `partials[warp_row][frame]`.
+ * 2 STS.64-equivalent + 2 LDS + 2 FADD per voice-sample instead of a 5-level
+ * shuffle tree per frame. */
+#define SKB_TILE_STRIDE 33   /* float2 units; +1 keeps the transposed read conflict-free */
+
+__global__ void __launch_bounds__(SKB_FREE_THREADS)
+k_render_free(const float4 *__restrict__ pq, float4 *__restrict__ sq, int cap, int n_slots,
+              const float *__restrict__ tables, const float *__restrict__ noise,
+              int nframes, unsigned long long ssc_before,
+              float2 *__restrict__ partials, int row_stride) {
+  __shared__ float2 tile[SKB_FREE_THREADS / 32][SKB_CHUNK * SKB_TILE_STRIDE];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slot = blockIdx.x * SKB_FREE_THREADS + threadIdx.x;
+  const int row = blockIdx.x * (SKB_FREE_THREADS / 32) + warp;
+  if ((slot & ~31) >= n_slots) return;           /* whole warp beyond the free range */
+  VoiceP p; VoiceS s; VoiceK k;
+  load_params(pq, cap, slot, p);
+  load_state(sq, cap, slot, s);
+  derive_consts(p, k);
+  const bool wants_noise = (p.flags & SKB_F_NOISE) != 0;
+  const NoMods nomods;
+  float2 *mytile = tile[warp];
+  float2 *out_row = partials + (size_t)row * row_stride;
+  for (int base = 0; base < nframes; base += SKB_CHUNK) {
+    const int cnt = min(SKB_CHUNK, nframes - base);
+    for (int f = 0; f < cnt; f++) {
+      const float white = wants_noise ? __ldg(noise + base + f) : 0.0f;
+      const float2 o = voice_frame<false>(p, k, s, ssc_before + (unsigned long long)(base + f + 1), white, tables, nomods);
+      mytile[f * SKB_TILE_STRIDE + lane] = o;
+    }
+    __syncwarp();
+    if (lane < cnt) {
+      float L = 0.0f, R = 0.0f;
+#pragma unroll
+      for (int v = 0; v < 32; v++) {
+        const float2 c = mytile[lane * SKB_TILE_STRIDE + v];
+        L += c.x; R += c.y;
+      }
+      out_row[base + lane] = make_float2(L, R);
+    }
+    __syncwarp();
+  }
+  store_state(sq, cap, slot, s);
+}
+
+/* ======================================================================== */
+/* K2  render_bins: modulation groups, frame-lock-step                       */
+/* ======================================================================== */
+/* A bin is one or more connected components of the F/A/P/C graph
+ * packed by the planner, voices in ascending voice-index order, one thread per
+ * voice.  voice_sample[] of the bin lives in shared memory, double buffered:
+ * a read of modulator m by voice n sees cur[m] when m < n (already rendered
+ * this frame) and prev[m] when m > n (synth.c:526 loop order).  `level` is the
+ * depth of a voice in the same-frame dependency DAG; levels run one after the
+ * other with a CTA barrier in between. */
+struct skb_bin_desc { int slot0, size, nlevels, row; };
+
+struct BinMods {
+  const float *prev, *cur, *inc;
+  __device__ __forceinline__ float read(int ref) const {
+    const int l = ref & SKB_REF_MASK;
+    return (ref & SKB_REF_CUR) ? cur[l] : prev[l];
+  }
+  __device__ __forceinline__ float inc_of(int ref) const { return inc[ref & SKB_REF_MASK]; }
+};
+
+__global__ void __launch_bounds__(1024)
+k_render_bins(const float4 *__restrict__ pq, float4 *__restrict__ sq, int cap,
+              const skb_bin_desc *__restrict__ bins,
+              const float *__restrict__ tables, const float *__restrict__ noise,
+              int nframes, unsigned long long ssc_before,
+              float2 *__restrict__ partials, int row_stride) {
+  extern __shared__ float bsm[];
+  const skb_bin_desc bd = bins[blockIdx.x];
+  const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  float *vs0 = bsm, *vs1 = bsm + nt, *incs = bsm + 2 * nt;
+  float2 *wsum = (float2 *)(bsm + 3 * nt);        /* [2][nwarps] */
+  const bool live = tid < bd.size;
+  const int slot = bd.slot0 + (live ? tid : 0);
+  VoiceP p; VoiceS s; VoiceK k;
+  load_params(pq, cap, slot, p);
+  load_state(sq, cap, slot, s);
+  derive_consts(p, k);
+  vs0[tid] = live ? s.sample : 0.0f;
+  vs1[tid] = 0.0f;
+  incs[tid] = live ? p.inc : 0.0f;
+  const bool wants_noise = live && (p.flags & SKB_F_NOISE);
+  float2 *out_row = partials + (size_t)bd.row * row_stride;
+  __syncthreads();
+  for (int f = 0; f < nframes; f++) {
+    BinMods mod;
+    mod.prev = (f & 1) ? vs1 : vs0;
+    float *cur = (f & 1) ? vs0 : vs1;
+    mod.cur = cur;
+    mod.inc = incs;
+    const float white = wants_noise ? __ldg(noise + f) : 0.0f;
+    float2 o = make_float2(0.0f, 0.0f);
+    for (int lvl = 0; lvl < bd.nlevels; lvl++) {
+      if (live && p.level == lvl) {
+        o = voice_frame<true>(p, k, s, ssc_before + (unsigned long long)(f + 1), white, tables, mod);
+        cur[tid] = s.sample;
+      }
+      __syncthreads();
+    }
+    /* fixed-order sum: xor butterfly inside the warp, then warps in order */
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      o.x += __shfl_xor_sync(0xffffffffu, o.x, d);
+      o.y += __shfl_xor_sync(0xffffffffu, o.y, d);
+    }
+    if (lane == 0) wsum[(f & 1) * nwarps + warp] = o;
+    if (f > 0 && tid == 0) {
+      float L = 0.0f, R = 0.0f;
+      const float2 *w = wsum + ((f - 1) & 1) * nwarps;
+      for (int i = 0; i < nwarps; i++) { L += w[i].x; R += w[i].y; }
+      out_row[f - 1] = make_float2(L, R);
+    }
+  }
+  __syncthreads();
+  if (tid == 0 && nframes > 0) {
+    float L = 0.0f, R = 0.0f;
+    const float2 *w = wsum + ((nframes - 1) & 1) * nwarps;
+    for (int i = 0; i < nwarps; i++) { L += w[i].x; R += w[i].y; }
+    out_row[nframes - 1] = make_float2(L, R);
+  }
+  if (live) store_state(sq, cap, slot, s);
+}
+
+/* ======================================================================== */
+/* K4  reduce_rows: partial rows -> raw stereo mix, fixed order              */
+/* ======================================================================== */
+#define SKB_RED_X 64
+#define SKB_RED_Y 8
+__global__ void __launch_bounds__(SKB_RED_X * SKB_RED_Y)
+k_reduce_rows(const float2 *__restrict__ partials, int rows, int nframes, int row_stride,
+              float2 *__restrict__ mix) {
+  __shared__ float2 acc[SKB_RED_Y][SKB_RED_X];
+  const int f = blockIdx.x * SKB_RED_X + threadIdx.x;
+  float L = 0.0f, R = 0.0f;
+  if (f < nframes)
+    for (int r = threadIdx.y; r < rows; r += SKB_RED_Y) {
+      const float2 c = partials[(size_t)r * row_stride + f];
+      L += c.x; R += c.y;
+    }
+  acc[threadIdx.y][threadIdx.x] = make_float2(L, R);
+  __syncthreads();
+  if (threadIdx.y == 0 && f < nframes) {
+    for (int y = 1; y < SKB_RED_Y; y++) { L += acc[y][threadIdx.x].x; R += acc[y][threadIdx.x].y; }
+    mix[f] = make_float2(L, R);
+  }
+}
+
+/* K5  master volume (synth.c:619-624): the one-pole trace `gain` is computed
+ * by the host in the reference's arithmetic; the device scales and stores. */
+__global__ void k_finish(const float2 *__restrict__ mix, const float *__restrict__ gain,
+                         float2 *__restrict__ out, int nframes) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < nframes) {
+    const float2 m = mix[f];
+    const float g = gain[f];
+    out[f] = make_float2(m.x * g, m.y * g);
+  }
+}
+
+/* ======================================================================== */
+/* K3  state edits at a block boundary                                       */
+/* ======================================================================== */
+/* ops are sorted (stably) by slot on the host; one thread replays one slot's
+ * run in order.  op.voice holds the SLOT here. */
+__device__ __forceinline__ void dev_apply_op(VoiceS &s, const skb_op &op) {
+  switch (op.code) {
+    case SKB_OP_TRIGGER:      s.finished = 0; s.phase = op.f0; break;                       /* synth.c:316-339 */
+    case SKB_OP_SET_FINISHED: s.finished = op.i0; break;                                    /* synth.c:281-282 */
+    case SKB_OP_ENV_ON:       s.env_start = op.u0; s.env_rel = 0ull; s.env_vel = op.f0; s.env_active = 1; break; /* :383-388 */
+    case SKB_OP_ENV_OFF:      if (s.env_active) s.env_rel = op.u0; break;                   /* :391-395 */
+    case SKB_OP_ENV_RESET:    s.env_start = 0ull; s.env_rel = 0ull; s.env_active = 0; break; /* :377-379 */
+    case SKB_OP_FILTER_CLEAR: s.x1 = s.x2 = s.y1 = s.y2 = 0.0f; break;                      /* :1017-1018 */
+    case SKB_OP_VOICE_CLEAR:  s.sample = 0.0f; s.sm_gain = 0.0f; break;                     /* :1094,1124 */
+    case SKB_OP_SET_PAN:      s.panL = op.f0; s.panR = op.f1; break;                        /* :841-842 */
+    case SKB_OP_SET_SH:       s.sh_count = op.i0; s.sh_hold = op.f0; break;                 /* :1045-1046 */
+    case SKB_OP_SET_PHASE:    s.phase = op.f0; break;
+    default: break;
+  }
+}
+
+__global__ void k_apply_ops(float4 *__restrict__ sq, int cap, const skb_op *__restrict__ ops,
+                            const int2 *__restrict__ runs, int nruns) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nruns) return;
+  const int2 r = runs[i];
+  const int slot = ops[r.x].voice;
+  VoiceS s;
+  load_state(sq, cap, slot, s);
+  for (int j = r.x; j < r.y; j++) dev_apply_op(s, ops[j]);
+  store_state(sq, cap, slot, s);
+}
+
+/* parameter records: recs[i][SKB_NPQ] float4 -> pq[k][slots[i]] */
+__global__ void k_scatter_params(float4 *__restrict__ pq, int cap, const int *__restrict__ slots,
+                                 const float4 *__restrict__ recs, int n) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * SKB_NPQ) return;
+  const int i = t / SKB_NPQ, k = t % SKB_NPQ;
+  pq[(size_t)k * cap + slots[i]] = recs[t];
+}
+
+/* re-plan: dst[k][s] = src[k][old_slot[s]] (zeros for a fresh slot) */
+__global__ void k_permute_state(const float4 *__restrict__ src, float4 *__restrict__ dst, int cap,
+                                const int *__restrict__ old_slot, int nslots) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nslots * SKB_NSQ) return;
+  const int k = t / nslots, sidx = t % nslots;
+  const int o = old_slot[sidx];
+  dst[(size_t)k * cap + sidx] = (o >= 0) ? src[(size_t)k * cap + o] : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__global__ void k_gather_state(const float4 *__restrict__ sq, int cap, const int *__restrict__ slots,
+                               int n, skb_voice_state *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  skb_voice_state o;
+  const int slot = slots[i];
+  if (slot < 0) {
+    memset(&o, 0, sizeof(o));
+  } else {
+    VoiceS s;
+    load_state(sq, cap, slot, s);
+    o.phase = s.phase; o.finished = s.finished; o.sample = s.sample; o.sh_hold = s.sh_hold;
+    o.sh_count = s.sh_count; o.x1 = s.x1; o.x2 = s.x2; o.y1 = s.y1; o.y2 = s.y2;
+    o.env_active = s.env_active; o.env_velocity = s.env_vel; o.smoother_gain = s.sm_gain;
+    o.pan_left = s.panL; o.pan_right = s.panR; o.env_start = s.env_start; o.env_release = s.env_rel;
+  }
+  out[i] = o;
+}
+
+__global__ void k_scatter_state(float4 *__restrict__ sq, int cap, const int *__restrict__ slots,
+                                int n, const skb_voice_state *__restrict__ in) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int slot = slots[i];
+  if (slot < 0) return;
+  const skb_voice_state o = in[i];
+  VoiceS s;
+  s.phase = o.phase; s.finished = o.finished; s.sample = o.sample; s.sh_hold = o.sh_hold;
+  s.sh_count = o.sh_count; s.x1 = o.x1; s.x2 = o.x2; s.y1 = o.y1; s.y2 = o.y2;
+  s.env_active = o.env_active; s.env_vel = o.env_velocity; s.sm_gain = o.smoother_gain;
+  s.panL = o.pan_left; s.panR = o.pan_right; s.env_start = o.env_start; s.env_rel = o.env_release;
+  store_state(sq, cap, slot, s);
+}

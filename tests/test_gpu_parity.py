@@ -1,0 +1,99 @@
+"""GPU: the CUDA engine behind the drop-in API versus the oracle.
+
+Bar (north_star): phase / table index / finished latch / event timing BIT-EXACT;
+floating-point outputs within 1e-5 of full scale (1.0) per sample.  The only
+float difference allowed by design is the ORDER of the cross-voice sum
+(DESIGN.md §Mix); everything per-voice is computed with the reference's own
+individually rounded IEEE ops.
+"""
+import numpy as np
+import pytest
+
+import cases
+from oracle import oracle as O
+from tests_util import PATCH_IDS, patch_lines, trace_render, assert_state_equal, FULL_SCALE_TOL
+
+pytestmark = pytest.mark.gpu
+
+# per-voice evolving words that never see a cross-voice sum: bit-exact unless a
+# modulator feeds them, in which case they inherit nothing inexact either (the
+# modulator is another voice's exact sample) — so exact everywhere.
+EXACT = ("phase", "finished", "sh_hold", "sh_count", "env_active", "env_start", "env_release",
+         "sample", "filter_xy", "smoother_gain", "pan_left", "pan_right")
+
+
+def maxdiff(a, b):
+    return float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64)))) if a.size else 0.0
+
+
+@pytest.mark.parametrize("n", PATCH_IDS)
+def test_patch_vs_golden(n, golden_patches):
+    s = O.DropinCuda(64)
+    s.load_lines(patch_lines(golden_patches, n))
+    gold = golden_patches["p%d_out" % n]
+    out, ph, fin = trace_render(s, gold.shape[0])
+    assert np.array_equal(ph.view(np.uint32), golden_patches["p%d_phase" % n].view(np.uint32)), "phase trace"
+    assert np.array_equal(fin, golden_patches["p%d_finished" % n]), "finished trace"
+    assert maxdiff(out, gold) <= FULL_SCALE_TOL
+
+
+@pytest.mark.parametrize("name", list(cases.SYNTHETIC))
+def test_synthetic_vs_golden(name, golden_synth, luts):
+    wl = cases.SYNTHETIC[name](luts)
+    s = O.DropinCuda(wl["voices"])
+    cases.drive_setup(s, wl)
+    out = cases.drive_render(s, wl)
+    st = s.state()
+    assert np.array_equal(st["phase"].view(np.uint32), golden_synth[name + "_phase"].view(np.uint32))
+    assert np.array_equal(st["finished"], golden_synth[name + "_finished"])
+    assert maxdiff(out, golden_synth[name + "_out"]) <= FULL_SCALE_TOL
+
+
+@pytest.mark.parametrize("name", list(cases.SYNTHETIC))
+def test_synthetic_vs_port_all_state(name, luts):
+    """Every evolving word of every voice, against the CPU restatement."""
+    wl = cases.SYNTHETIC[name](luts)
+    a, b = O.PortSkred(wl["voices"]), O.DropinCuda(wl["voices"])
+    for s in (a, b):
+        cases.drive_setup(s, wl)
+    oa, ob = cases.drive_render(a, wl), cases.drive_render(b, wl)
+    assert maxdiff(oa, ob) <= FULL_SCALE_TOL
+    assert_state_equal(a.state(), b.state(), exact_keys=EXACT)
+
+
+def test_config1_0sk_full_10s(golden_patches):
+    """BASELINE configs[0]: 0.sk, 10 s at 44.1 kHz = 861 callbacks of 512 + a 168-frame tail."""
+    lines = patch_lines(golden_patches, 0)
+    ref = O.RefSkred(64) if O.have_ref(64) else O.PortSkred(64)
+    gpu = O.DropinCuda(64)
+    ref.load_lines(lines)
+    gpu.load_lines(lines)
+    a, pa, _ = trace_render(ref, 441000)
+    b, pb, _ = trace_render(gpu, 441000)
+    assert np.array_equal(pa[:, :2].view(np.uint32), pb[:, :2].view(np.uint32)), "voice_phase[0..1] at every block end"
+    assert maxdiff(a, b) <= FULL_SCALE_TOL
+    assert abs(float(np.abs(a).max()) - 0.05) < 1e-3
+
+
+@pytest.mark.parametrize("n", [1, 15, 23, 26, 42, 64, 73])
+def test_patch_2s_vs_oracle(n, golden_patches):
+    lines = patch_lines(golden_patches, n)
+    ref = O.RefSkred(64) if O.have_ref(64) else O.PortSkred(64)
+    gpu = O.DropinCuda(64)
+    ref.load_lines(lines)
+    gpu.load_lines(lines)
+    a, b = ref.render(88200), gpu.render(88200)
+    assert maxdiff(a, b) <= FULL_SCALE_TOL
+    assert_state_equal(ref.state(), gpu.state(), exact_keys=EXACT)
+
+
+def test_big_callbacks_equal_small_callbacks(luts):
+    """synth(4096) == 8 x synth(512) when no event falls inside (batch mode)."""
+    wl = cases.SYNTHETIC["korg_cz_filter"](luts)
+    a, b = O.DropinCuda(64, run_seq=False), O.DropinCuda(64, run_seq=False)
+    for s in (a, b):
+        cases.drive_setup(s, wl)
+    oa = a.render(8192, block=512)
+    ob = b.render(8192, block=4096)
+    assert np.array_equal(oa.view(np.uint32), ob.view(np.uint32))
+    assert_state_equal(a.state(), b.state())

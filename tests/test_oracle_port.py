@@ -1,0 +1,68 @@
+"""CPU: pin the oracle.  The restatement (oracle/skred_port.c behind the product's
+host shim) must equal the compiled reference (oracle/_ref) BIT FOR BIT, and both
+must equal the committed golden fixtures generated from the reference."""
+import numpy as np
+import pytest
+
+import cases
+from oracle import oracle as O
+from tests_util import PATCH_IDS, patch_lines, trace_render, assert_state_equal
+
+needs_ref = pytest.mark.skipif(not O.have_ref(64), reason="compiled reference (oracle/_ref) not present")
+
+
+@pytest.mark.parametrize("n", PATCH_IDS)
+def test_port_matches_golden_patch(n, golden_patches):
+    s = O.PortSkred(64)
+    s.load_lines(patch_lines(golden_patches, n))
+    out, ph, fin = trace_render(s, golden_patches["p%d_out" % n].shape[0])
+    assert np.array_equal(out.view(np.uint32), golden_patches["p%d_out" % n].view(np.uint32))
+    assert np.array_equal(ph.view(np.uint32), golden_patches["p%d_phase" % n].view(np.uint32))
+    assert np.array_equal(fin, golden_patches["p%d_finished" % n])
+
+
+@pytest.mark.parametrize("name", list(cases.SYNTHETIC))
+def test_port_matches_golden_synthetic(name, golden_synth, luts):
+    wl = cases.SYNTHETIC[name](luts)
+    s = O.PortSkred(wl["voices"])
+    cases.drive_setup(s, wl)
+    out = cases.drive_render(s, wl)
+    st = s.state()
+    assert np.array_equal(out.view(np.uint32), golden_synth[name + "_out"].view(np.uint32))
+    assert np.array_equal(st["phase"].view(np.uint32), golden_synth[name + "_phase"].view(np.uint32))
+    assert np.array_equal(st["finished"], golden_synth[name + "_finished"])
+
+
+@needs_ref
+@pytest.mark.parametrize("n", PATCH_IDS)
+def test_reference_matches_golden_patch(n, golden_patches):
+    s = O.RefSkred(64)
+    s.load_lines(patch_lines(golden_patches, n))
+    out, ph, fin = trace_render(s, golden_patches["p%d_out" % n].shape[0])
+    assert np.array_equal(out.view(np.uint32), golden_patches["p%d_out" % n].view(np.uint32))
+    assert np.array_equal(ph.view(np.uint32), golden_patches["p%d_phase" % n].view(np.uint32))
+
+
+@needs_ref
+@pytest.mark.parametrize("n", [0, 15, 26, 42, 64])
+def test_port_matches_reference_long(n, golden_patches):
+    """2 s of audio incl. sequencer-driven events, every evolving word compared."""
+    a, b = O.RefSkred(64), O.PortSkred(64)
+    lines = patch_lines(golden_patches, n)
+    a.load_lines(lines)
+    b.load_lines(lines)
+    oa, ob = a.render(88200), b.render(88200)
+    assert np.array_equal(oa.view(np.uint32), ob.view(np.uint32))
+    assert_state_equal(a.state(), b.state())
+
+
+@needs_ref
+@pytest.mark.parametrize("name", list(cases.SYNTHETIC))
+def test_port_matches_reference_synthetic_state(name, luts):
+    wl = cases.SYNTHETIC[name](luts)
+    a, b = O.RefSkred(64), O.PortSkred(64)
+    for s in (a, b):
+        cases.drive_setup(s, wl)
+    oa, ob = cases.drive_render(a, wl), cases.drive_render(b, wl)
+    assert np.array_equal(oa.view(np.uint32), ob.view(np.uint32))
+    assert_state_equal(a.state(), b.state())
