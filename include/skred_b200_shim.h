@@ -49,6 +49,34 @@ int  skb_shim_snapshot_range(int first, int n);
 void skb_shim_mark_dirty(int voice);
 void skb_shim_scan_all(int on);
 
+/* Timestamped event batch — the binary twin of the reference's work_queue[] +
+ * seq() (seq.c:164-178, 241-257; wire.c:869-892 computes `when`).  `when` is an
+ * absolute sample time; an event fires after the 512-frame sub-block ending at
+ * count c when `when <= c + 512` by calling the setter its code
+ * names, exactly as seq() would re-parse the deferred wire string.  synth()
+ * with num_frames > 512 is cut only at boundaries where something fires. */
+enum {
+  SKB_EV_TRIGGER = 1,   /* T        voice_trigger (+ link_trig), wire.c:710-714 */
+  SKB_EV_VELOCITY,      /* l<a0>    envelope_velocity (+ link_velo), wire.c:674-679 */
+  SKB_EV_FREQ,          /* f<a0>    freq_set */
+  SKB_EV_MIDI,          /* n<a0>    freq_midi (+ link_midi), wire.c:682-687 */
+  SKB_EV_AMP,           /* a<a0>    amp_set */
+  SKB_EV_PAN,           /* p<a0>    pan_set */
+  SKB_EV_WAVE,          /* w<a0>    wave_set */
+  SKB_EV_CZ,            /* c<a0>,<a1> cz_set */
+  SKB_EV_FILTER_FREQ,   /* K<a0>    mmf_set_freq */
+  SKB_EV_FILTER_RES,    /* Q<a0>    mmf_set_res */
+  SKB_EV_MUTE,          /* m<a0>    wave_mute */
+};
+typedef struct skb_event {
+  uint64_t when;
+  int32_t  voice;
+  int32_t  code;
+  float    a0, a1;
+} skb_event;            /* 24 bytes */
+int  skb_shim_queue_events(const skb_event *ev, int n);
+int  skb_shim_pending_events(void);
+
 /* A wave slot edited in place (wave_table_dynamic_expand, wire.c:553-586)
  * must be re-uploaded at its next `w`. */
 void skb_shim_wave_touch(int wave);

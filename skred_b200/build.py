@@ -33,7 +33,8 @@ NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 # arithmetic `gcc -O2 -ffp-contract=off` gives the reference on x86-64.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-              "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v",
+              "-Xlinker", "-soname=libskred_b200.so"]
 HOST_CFLAGS = ["-O2", "-ffp-contract=off", "-fPIC", "-fno-strict-aliasing", "-g1"]
 DEFAULT_VOICES = [64, 1024, 4096, 65536]
 

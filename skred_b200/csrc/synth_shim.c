@@ -926,6 +926,91 @@ static void mark_latency(void) {
     if (voice_mark_go[v]) { clock_gettime(CLOCK_MONOTONIC, &voice_mark_b[v]); voice_mark_go[v] = 0; }
 }
 
+/* ---- timestamped event queue ------------------------------------------------
+ * The binary twin of the reference's work_queue[] + seq() (seq.c:164-178,
+ * 241-257): events carry an absolute sample time; after every callback-sized
+ * sub-block ending at count c they fire when `when <= c + frames`
+ * by calling the ordinary setters, so they reach the device as parameter
+ * records / ordered ops at that block boundary.  Unlike work_queue (1,024
+ * strings, silently dropping when full) the queue is unbounded. */
+static skb_event *g_evq = NULL;
+static size_t g_evq_head = 0, g_evq_n = 0, g_evq_cap = 0;
+static uint64_t g_events_fired = 0;
+
+int skb_shim_queue_events(const skb_event *ev, int n) {
+  if (n < 0 || (n > 0 && !ev)) return SKB_ERR_ARG;
+  if (g_evq_head > 0 && g_evq_head == g_evq_n) g_evq_head = g_evq_n = 0;
+  if (g_evq_n + (size_t)n > g_evq_cap) {
+    g_evq_cap = (g_evq_n + (size_t)n) * 2 + 1024;
+    g_evq = (skb_event *)realloc(g_evq, g_evq_cap * sizeof(skb_event));
+  }
+  /* keep the queue ordered by `when`, first-come first-served among equals
+   * (seq() scans work_queue in slot order; equal-time items fire in queue order) */
+  for (int i = 0; i < n; i++) {
+    size_t j = g_evq_n;
+    while (j > g_evq_head && g_evq[j - 1].when > ev[i].when) { g_evq[j] = g_evq[j - 1]; j--; }
+    g_evq[j] = ev[i];
+    g_evq_n++;
+  }
+  return SKB_OK;
+}
+
+int skb_shim_pending_events(void) { return (int)(g_evq_n - g_evq_head); }
+
+static void fire_event(const skb_event *e) {
+  const int v = e->voice;
+  if (v < 0 || v >= VOICE_MAX) return;
+  switch (e->code) {
+    case SKB_EV_TRIGGER:     voice_trigger(v); if (voice_link_trig[v] > 0) voice_trigger(voice_link_trig[v]); break;  /* wire.c:710-714 */
+    case SKB_EV_VELOCITY:    envelope_velocity(v, e->a0);                                                     /* wire.c:674-679 */
+                             if (voice_link_velo_a[v] >= 0) envelope_velocity(voice_link_velo_a[v], e->a0);
+                             if (voice_link_velo_b[v] >= 0) envelope_velocity(voice_link_velo_b[v], e->a0); break;
+    case SKB_EV_FREQ:        freq_set(v, e->a0); break;
+    case SKB_EV_MIDI:        freq_midi(v, e->a0);                                                             /* wire.c:682-687 */
+                             if (voice_link_midi_a[v] >= 0) freq_midi(voice_link_midi_a[v], e->a0);
+                             if (voice_link_midi_b[v] >= 0) freq_midi(voice_link_midi_b[v], e->a0); break;
+    case SKB_EV_AMP:         amp_set(v, e->a0); break;
+    case SKB_EV_PAN:         pan_set(v, e->a0); break;
+    case SKB_EV_WAVE:        wave_set(v, (int)e->a0); break;
+    case SKB_EV_CZ:          cz_set(v, (int)e->a0, e->a1); break;
+    case SKB_EV_FILTER_FREQ: mmf_set_freq(v, e->a0); break;
+    case SKB_EV_FILTER_RES:  mmf_set_res(v, e->a0); break;
+    case SKB_EV_MUTE:        wave_mute(v, (int)e->a0); break;
+    default: break;
+  }
+}
+
+/* seq()'s firing rule for the callback that just ended (seq.c:171-178). */
+static void fire_due(int frame_count) {
+  const uint64_t horizon = synth_sample_count + (uint64_t)frame_count;
+  while (g_evq_head < g_evq_n && g_evq[g_evq_head].when <= horizon) {
+    fire_event(&g_evq[g_evq_head++]);
+    g_events_fired++;
+  }
+}
+
+/* First sub-block boundary (relative to the call start, in (done, num_frames])
+ * after which the head of the queue fires; num_frames + 1 if none does. */
+static int next_firing_boundary(int done, int num_frames, uint64_t start_count) {
+  if (g_evq_head >= g_evq_n) return num_frames + 1;
+  const int EB = SYNTH_FRAMES_PER_CALLBACK;
+  const uint64_t w = g_evq[g_evq_head].when;
+  for (int b = (done / EB + 1) * EB;; b += EB) {
+    const int end = b < num_frames ? b : num_frames;
+    const int len = end - (b - EB);
+    if (w <= start_count + (uint64_t)end + (uint64_t)len) return end;
+    if (end == num_frames) break;
+  }
+  return num_frames + 1;
+}
+
+static void render_segment(float *buffer, int num_channels, int n) {
+  step_traces(n);
+  int r = skb_render(g_engine, n, synth_sample_count, g_gain, g_noise, buffer, num_channels);
+  if (r != SKB_OK) shim_die("skb_render");
+  synth_sample_count += (uint64_t)n;
+}
+
 void synth(float *buffer, float *input, int num_frames, int num_channels, void *user) {
   (void)input; (void)user;   /* the per-voice tap `user` is opt-in: see skb_shim_* docs */
   static int first = 1;
@@ -936,16 +1021,23 @@ void synth(float *buffer, float *input, int num_frames, int num_channels, void *
 
   engine();
   mark_latency();
-  if (skb_shim_flush() != SKB_OK) shim_die("flush");
+  const int EB = SYNTH_FRAMES_PER_CALLBACK;
+  const uint64_t start_count = synth_sample_count;
   int done = 0;
   while (done < num_frames) {
-    const int n = (num_frames - done) < g_cfg_max_frames ? (num_frames - done) : g_cfg_max_frames;
-    step_traces(n);
-    int r = skb_render(g_engine, n, synth_sample_count, g_gain, g_noise,
-                       buffer + (size_t)done * num_channels, num_channels);
-    if (r != SKB_OK) shim_die("skb_render");
-    synth_sample_count += (uint64_t)n;
-    done += n;
+    /* render up to the next boundary at which a queued event fires (everything
+     * in between is event-free, so one long launch equals many callbacks) */
+    int end = next_firing_boundary(done, num_frames, start_count);
+    const int fires = end <= num_frames;
+    if (!fires) end = num_frames;
+    if (end - done > g_cfg_max_frames) end = done + g_cfg_max_frames;
+    if (skb_shim_flush() != SKB_OK) shim_die("flush");
+    render_segment(buffer + (size_t)done * num_channels, num_channels, end - done);
+    if (fires && end - done > 0) {
+      const int sub = (end % EB) ? (end % EB) : EB;     /* length of the sub-block that just ended */
+      fire_due(sub);
+    }
+    done = end;
   }
   clock_gettime(CLOCK_MONOTONIC, &g_bench[slot].b);
   g_bench[slot].state = 2;
@@ -963,6 +1055,7 @@ int skb_shim_render_mix(int num_frames, float *d_mix, void *stream) {
   step_traces(num_frames);
   int r = skb_render_mix(g_engine, num_frames, synth_sample_count, g_noise, d_mix, stream);
   synth_sample_count += (uint64_t)num_frames;
+  fire_due(num_frames);        /* seq()'s rule for this callback */
   return r;
 }
 
