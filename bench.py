@@ -1,0 +1,404 @@
+#!/usr/bin/env python3
+"""bench.py — voice-samples/s of the per-voice render path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  torchrun --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE configs[4] — 65,536 voices, the mixed
+config-2 / config-3 / config-4 recipe by v%3 (LUT + ADSR + pan, Korg + CZ +
+resonant biquad + ADSR, AMY one-shot PCM with pitch shift), amplitudes 40/V,
+one (re)trigger per voice per 10 s as timestamped events applied at 512-frame
+block boundaries.  One STEP = one batch of `--frames` frames
+(default 4096 = 8 reference callbacks) of all voices.
+
+  value   device-resident: params/state/tables/pending events live in HBM; K steps of
+          skb_shim_render_mix (+ NCCL reduce of the stereo partial mixes for N > 1),
+          CUDA events on the launching stream, max over ranks.
+  e2e     the call a skred host makes: synth(buffer, NULL, frames, 2, NULL) with a HOST
+          buffer — event firing, parameter/op/trace H2D, kernels, D2H of the block
+          inside the timed region (N > 1: render_mix -> reduce -> finish on rank 0).
+  cpu_baseline  the compiled reference (oracle/_ref) on ONE host core over a bounded
+          sample (first 4096 voices of the same load).
+
+`--impl reference` times the reference's own synth.c (oracle/_ref, pinned flags)
+voice-sharded over ALL host cores (independent processes — the reference is
+single-threaded) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from skred_b200 import workloads as W  # noqa: E402
+
+SR = 44100
+METRIC = "voice-samples/sec (osc+filter+env+mix)"
+UNIT = "voice-samples/s"
+# algorithmic traffic 276 B per voice per 512-frame block = 0.54 B per voice-sample
+# (224 B parameter + state read, 52 B state write); per launch of F frames: 276 B per voice + 8 B per frame.
+BYTES_PER_VOICE_LAUNCH = 276.0
+# individually rounded fp32 ops per voice-sample (no FMA in parity mode):
+# 15 for a plain LUT/PCM voice, 32 for Korg + CZ + biquad; config 5 mixes them 2:1.
+FLOPS_PER_VOICE_SAMPLE = (15.0 * 2 + 32.0) / 3.0
+FP32_LANES_PER_SM = 128
+N_SM = 148
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("hbm_gbs", 6650.0)), float(d.get("sm_max_mhz", 1965.0)), "measured"
+    return 6650.0, 1965.0, "fallback"
+
+
+def load_luts():
+    p = os.path.join(ROOT, "tests", "golden", "notamy_luts.npz")
+    return dict(np.load(p)) if os.path.exists(p) else None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- #
+# reference arm / CPU baseline: the compiled reference on host cores           #
+# --------------------------------------------------------------------------- #
+def _ref_worker(args):
+    """One process = one independent instance of the reference (VOICE_MAX = shard size)
+    rendering voices [v0, v0 + shard) of the V-voice load."""
+    V, shard, v0, frames_per_step, steps, warmup, event_seconds = args
+    from oracle import oracle as O
+    wl = W.config5(V, seconds=600.0, luts=load_luts(), event_seconds=event_seconds)
+    s = O.RefSkred(shard, run_seq=False)
+    for slot, (data, kw) in wl["tables"].items():
+        from skred_b200.host import install_table
+        install_table(s, slot, data, **kw)
+    s.apply([(c[0], c[1] - v0) + tuple(c[2:]) for c in wl["setup"] if v0 <= c[1] < v0 + shard])
+    ev = {}
+    for k, calls in wl["events"].items():
+        mine = [(c[0], c[1] - v0) + tuple(c[2:]) for c in calls if v0 <= c[1] < v0 + shard]
+        if mine:
+            ev[k] = mine
+    out = np.zeros((frames_per_step, 2), dtype=np.float32)
+    times = []
+    k = 0
+    for step in range(warmup + steps):
+        t0 = time.perf_counter()
+        done = 0
+        while done < frames_per_step:
+            if k in ev:
+                s.apply(ev[k])
+            s._synth(out[done:done + 512], 512)
+            done += 512
+            k += 1
+        times.append(time.perf_counter() - t0)
+    return times[warmup:]
+
+
+def run_reference_cpu(V, frames_per_step, steps, warmup, procs, shard=4096, voices_limit=None):
+    """Returns (voice-samples/s, seconds per step, voices rendered, procs)."""
+    import multiprocessing as mp
+    nshards = (voices_limit or V) // shard
+    jobs = [(V, shard, i * shard, frames_per_step, steps, warmup, 30.0) for i in range(nshards)]
+    procs = max(1, min(procs, nshards))
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_ref_worker, jobs, chunksize=1)
+    wall = time.perf_counter() - t0
+    # shards run `procs` at a time: step time of the job = sum over waves of the slowest shard
+    per_step = np.zeros(steps)
+    for w0 in range(0, nshards, procs):
+        per_step += np.max(np.array(res[w0:w0 + procs]), axis=0)
+    sec = float(np.mean(per_step))
+    voices = nshards * shard
+    return voices * frames_per_step / sec, sec, voices, procs, wall
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    V = a.voices
+    shard = 4096 if V >= 4096 else V
+    from oracle import oracle as O
+    if not O.have_ref(shard):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libskred_ref_v%d.so not built" % shard}))
+        return 0
+    cores = os.cpu_count() or 1
+    frames = 512 if a.ref_frames is None else a.ref_frames          # bounded sample: one callback per step
+    vps, sec, voices, procs, wall = run_reference_cpu(V, frames, a.steps, a.warmup, cores, shard)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": vps, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config5: %d voices mixed LUT/Korg+CZ+biquad/PCM, sparse retrigger events" % V,
+                   "voices": voices, "frames_per_step": frames,
+                   "parallelism": "%d independent reference processes x %d voices (reference is single-threaded)" % (procs, shard)},
+        "cpu_baseline": {"value": vps, "unit": UNIT, "cores": procs, "kind": "reference",
+                         "sample": "%d voices x %d frames per step, %d steps; synth.c compiled gcc -O2 -ffp-contract=off" % (voices, frames, a.steps)},
+        "e2e": {"value": vps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------- #
+# own arm                                                                      #
+# --------------------------------------------------------------------------- #
+def own_arm(a):
+    import torch
+    import torch.distributed as dist
+    from skred_b200 import Skred
+    from skred_b200.host import load_engine_lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    V, F = a.voices, a.frames
+    hbm_peak, sm_mhz, peak_kind = load_peaks()
+
+    sk = Skred(V, device=local, rank=rank, world=world, max_frames=max(F, 512))
+    total_frames = (a.warmup + a.steps) * F * 2 + 4 * F
+    wl = W.config5(V, seconds=600.0, luts=load_luts(), event_seconds=total_frames / SR + 1.0)
+    W.install(sk, wl)
+    ev = W.to_skb_events(wl["timed"])
+    sk.lib.skb_shim_queue_events.argtypes = [C.c_void_p, C.c_int]
+    sk.lib.skb_shim_queue_events(ev.ctypes.data, len(ev))
+    sk.flush()
+    eng = load_engine_lib()
+    st0 = sk.stats()
+    owned = st0.n_owned_voices if world > 1 else V
+
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+    d_mix = torch.zeros((F, 2), dtype=torch.float32, device="cuda")
+    out = np.zeros((F, 2), dtype=np.float32)
+
+    LF = a.launch_frames                     # frames per launch: events land on 512-frame boundaries
+    mix_ptr = d_mix.data_ptr()
+
+    def render_step():
+        for b in range(0, F, LF):
+            sk.render_mix(LF, mix_ptr + b * 8, sp)
+
+    def step_device():
+        render_step()
+        if world > 1:
+            dist.reduce(d_mix, dst=0, op=dist.ReduceOp.SUM)
+
+    def step_e2e():
+        if world == 1:
+            sk.lib.synth(out.ctypes.data, None, F, 2, None)
+        else:
+            render_step()
+            dist.reduce(d_mix, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                sk.finish(mix_ptr, F, out, sp)
+            else:
+                sk.lib.skb_shim_discard_gain()
+                eng.skb_sync(sk.engine, sp)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident value ------------------------------------------------
+    for _ in range(a.warmup):
+        step_device()
+        sk.lib.skb_shim_discard_gain()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    s_before = sk.stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms = []
+    e0.record(stream)
+    for _ in range(a.steps):
+        step_device()
+        sk.lib.skb_shim_discard_gain()
+    e1.record(stream)
+    barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    s_after = sk.stats()
+    launches = int(s_after.kernel_launches - s_before.kernel_launches) + (a.steps if world > 1 else 0)
+
+    # dominant kernel alone (k_render_free + bins + reduce), CUDA events inside the engine
+    for _ in range(3):
+        step_device()
+        sk.lib.skb_shim_discard_gain()
+        eng.skb_sync(sk.engine, sp)
+        kern_ms.append(sk.stats().last_render_ms)
+    barrier()
+    sk.lib.skb_shim_discard_gain()
+
+    # ---- end to end through synth() ---------------------------------------------
+    for _ in range(a.warmup):
+        step_e2e()
+    barrier()
+    s_b = sk.stats()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step_e2e()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    s_a = sk.stats()
+    clk = clocks.stop() if rank == 0 else None
+    ops = int(s_a.ops_applied - s_b.ops_applied)
+    par = int(s_a.params_uploaded - s_b.params_uploaded)
+    h2d = (ops * 32 + par * 132 + a.steps * F * 4) / a.steps
+    d2h = F * 8
+
+    value = V * F * a.steps / (dev_ms * 1e-3)
+    e2e = V * F * a.steps / e2e_s
+    k_ms = float(np.mean(kern_ms))
+    algo_bytes = owned * BYTES_PER_VOICE_LAUNCH + LF * 8
+    ach_gbs = algo_bytes / (k_ms * 1e-3) / 1e9
+    fp32_peak = N_SM * FP32_LANES_PER_SM * sm_mhz * 1e6
+    ach_flops = owned * LF * FLOPS_PER_VOICE_SAMPLE / (k_ms * 1e-3)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config5: %d voices mixed LUT/Korg+CZ+biquad/PCM, sparse retrigger events" % V,
+                       "voices": V, "frames_per_step": F, "frames_per_launch": LF, "block_frames": 512,
+                       "parallelism": "voice-sharded x%d, NCCL reduce of stereo partials" % world if world > 1 else "1 GPU",
+                       "l2": "state+params %.1f MB per launch, each word touched once per launch (no reuse to cache)" % (owned * 276 / 1e6)},
+            "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                         "traffic": None, "peak_kind": peak_kind, "kernel": "k_render_free(+k_render_bins,+k_reduce_rows)",
+                         "kernel_ms": k_ms,
+                         "note": "the path is FP32-issue bound, not HBM bound (SURVEY 8d): see roofline_fp32"},
+            "roofline_fp32": {"bound": "fp32-issue (no FMA: parity mode rounds every op)", "achieved": ach_flops / 1e12,
+                              "peak": fp32_peak / 1e12, "unit": "Tflop/s (1 op per lane-issue)",
+                              "frac": ach_flops / fp32_peak, "flops_per_voice_sample": FLOPS_PER_VOICE_SAMPLE},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_s / a.steps * 1e3, "api": "synth(buffer, NULL, %d, 2, NULL)" % F},
+            "gpu_launches": launches,
+            "clocks": clk,
+            "block_latency_ms_p50": None,
+        }
+        if world == 1 and not a.no_latency:
+            line["block_latency_ms_p50"] = block_latency(sk, a.latency_blocks)
+        if world == 1 and not a.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(V)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def block_latency(sk, nblocks):
+    """p50 host-observed time of one synth() call of 512 frames (event flush -> kernels -> 4 KiB D2H)."""
+    out = np.zeros((512, 2), dtype=np.float32)
+    ts = []
+    for _ in range(nblocks):
+        t0 = time.perf_counter()
+        sk.lib.synth(out.ctypes.data, None, 512, 2, None)
+        ts.append(time.perf_counter() - t0)
+    return float(np.median(ts) * 1e3)
+
+
+def cpu_baseline(V):
+    from oracle import oracle as O
+    shard = 4096 if V >= 4096 else V
+    if not O.have_ref(shard):
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+    frames, steps = 2048, 3
+    vps, sec, voices, procs, wall = run_reference_cpu(V, frames, steps, 1, 1, shard, voices_limit=shard)
+    return {"value": vps, "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": "first %d voices of the same load x %d frames x %d steps (%.1f s of CPU), synth.c gcc -O2 -ffp-contract=off"
+                      % (voices, frames, steps, wall)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--voices", type=int, default=65536)
+    ap.add_argument("--frames", type=int, default=4096, help="frames per step (multiple of 512)")
+    ap.add_argument("--launch-frames", type=int, default=512)
+    ap.add_argument("--ref-frames", type=int, default=None)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--latency-blocks", type=int, default=1000)
+    a = ap.parse_args()
+    if a.warmup < 3:
+        a.warmup = 3
+    if a.impl == "reference":
+        return reference_arm(a)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(a.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return own_arm(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -87,6 +87,9 @@ void skb_shim_wave_touch(int wave);
  * across GPUs (ncclReduce over NVLink) the root calls skb_shim_finish. */
 int  skb_shim_render_mix(int num_frames, float *d_mix, void *stream);
 int  skb_shim_finish(const float *d_mix, int num_frames, float *out, int num_channels, void *stream);
+/* A non-root rank (or a caller that keeps the raw mix on the device) drops the
+ * master-volume trace accumulated by its skb_shim_render_mix calls. */
+void skb_shim_discard_gain(void);
 
 #ifdef __cplusplus
 }

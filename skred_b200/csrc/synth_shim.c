@@ -908,14 +908,18 @@ static void ensure_traces(int n) {
 /* Advance the two voice-independent recurrences of the frame loop for
  * `n` frames: the shared noise draw (synth.c:525) and the master-volume
  * one-pole (synth.c:616-617).  Returns non-zero if any voice needs noise. */
-static int step_traces(int n) {
-  ensure_traces(n);
+static int g_gain_fill = 0;   /* split form: gain frames rendered but not yet finished */
+
+static int step_traces(int n, int append) {
+  const int base = append ? g_gain_fill : 0;
+  ensure_traces(base + n);
   if (!g_rng_seeded) { audio_rng_init(&g_rng, 1); g_rng_seeded = 1; }      /* synth.c:508 */
   for (int i = 0; i < n; i++) g_noise[i] = audio_rng_float(&g_rng);
   float g = volume_smoother_gain;
   const float k = volume_smoother_smoothing, target = volume_final;
-  for (int i = 0; i < n; i++) { g += k * (target - g); g_gain[i] = g; }
+  for (int i = 0; i < n; i++) { g += k * (target - g); g_gain[base + i] = g; }
   volume_smoother_gain = g;
+  g_gain_fill = base + n;
   return 1;
 }
 
@@ -1005,7 +1009,7 @@ static int next_firing_boundary(int done, int num_frames, uint64_t start_count) 
 }
 
 static void render_segment(float *buffer, int num_channels, int n) {
-  step_traces(n);
+  step_traces(n, 0);
   int r = skb_render(g_engine, n, synth_sample_count, g_gain, g_noise, buffer, num_channels);
   if (r != SKB_OK) shim_die("skb_render");
   synth_sample_count += (uint64_t)n;
@@ -1047,18 +1051,25 @@ void synth(float *buffer, float *input, int num_frames, int num_channels, void *
 /* Split form of synth() for multi-GPU hosts: flush + render this engine's
  * voices into DEVICE memory d_mix[num_frames][2]; after the caller reduced the
  * partial mixes over NVLink, skb_shim_finish applies the master volume on the
- * root.  Both advance / consume the host traces exactly like synth(). */
+ * root.  Both advance / consume the host traces exactly like synth().  Several
+ * render_mix calls (one per 512-frame callback) may precede one finish over
+ * their concatenated frames (batch mode reduces once per multi-block chunk). */
 int skb_shim_render_mix(int num_frames, float *d_mix, void *stream) {
   engine();
   if (num_frames > g_cfg_max_frames) return SKB_ERR_ARG;
   if (skb_shim_flush() != SKB_OK) return skb_last_error(g_engine);
-  step_traces(num_frames);
+  step_traces(num_frames, 1);
   int r = skb_render_mix(g_engine, num_frames, synth_sample_count, g_noise, d_mix, stream);
   synth_sample_count += (uint64_t)num_frames;
   fire_due(num_frames);        /* seq()'s rule for this callback */
   return r;
 }
 
+void skb_shim_discard_gain(void) { g_gain_fill = 0; }
+
 int skb_shim_finish(const float *d_mix, int num_frames, float *out, int num_channels, void *stream) {
+  /* consumes the gain trace of every skb_shim_render_mix since the last finish */
+  if (num_frames != g_gain_fill) return SKB_ERR_STATE;
+  g_gain_fill = 0;
   return skb_finish(engine(), d_mix, num_frames, g_gain, out, num_channels, stream);
 }

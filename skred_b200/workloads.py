@@ -18,12 +18,33 @@ SR = 44100
 
 def callback_for_time(when_samples, block=BLOCK):
     """F8: seq() after the callback ending at count c fires items with
-    when <= c + block; they are audible from callback index c/block."""
-    return max(0, -(-int(when_samples) // block) - 1)
+    when <= c + block; they are audible from callback index c/block.  The first
+    seq() runs after callback 0, so nothing queued can land before callback 1."""
+    return max(1, -(-int(when_samples) // block) - 1)
 
 
-def _add(events, k, call):
-    events.setdefault(k, []).append(call)
+EVENT_CODES = {"voice_trigger": 1, "envelope_velocity": 2, "freq_set": 3, "freq_midi": 4, "amp_set": 5,
+               "pan_set": 6, "wave_set": 7, "cz_set": 8, "mmf_set_freq": 9, "mmf_set_res": 10, "wave_mute": 11}
+
+
+def bucket(timed, block=BLOCK):
+    """[(when, call)] -> {callback_index: [call, ...]} under the F8 rule."""
+    ev = {}
+    for when, call in sorted(timed, key=lambda x: x[0]):
+        ev.setdefault(callback_for_time(when, block), []).append(call)
+    return ev
+
+
+def to_skb_events(timed):
+    """[(when, call)] -> structured array matching `skb_event` (include/skred_b200_shim.h)."""
+    import numpy as np
+    dt = np.dtype([("when", "<u8"), ("voice", "<i4"), ("code", "<i4"), ("a0", "<f4"), ("a1", "<f4")])
+    timed = sorted(timed, key=lambda x: x[0])
+    a = np.zeros(len(timed), dtype=dt)
+    for i, (when, call) in enumerate(timed):
+        a[i] = (when, call[1], EVENT_CODES[call[0]], call[2] if len(call) > 2 else 0.0,
+                call[3] if len(call) > 3 else 0.0)
+    return a
 
 
 class XorShift64:
@@ -85,14 +106,15 @@ def config2(V=64, seconds=60.0, luts=None):
     setup = []
     for v in range(V):
         setup += lut_voice(v, V, luts is not None)
-    events = {}
+    timed = []
     for v in range(V):
         if seconds > 30.0:
-            _add(events, callback_for_time(30 * SR), ("envelope_velocity", v, 0.0))
+            timed.append((30 * SR, ("envelope_velocity", v, 0.0)))
         if seconds > 31.0:
-            _add(events, callback_for_time(31 * SR), ("envelope_velocity", v, 1.0))
+            timed.append((31 * SR, ("envelope_velocity", v, 1.0)))
+    timed.sort(key=lambda x: x[0])
     return {"name": "config2_lut_adsr_pan", "voices": V, "tables": tables, "setup": setup,
-            "events": events, "frames": int(seconds * SR)}
+            "timed": timed, "events": bucket(timed), "frames": int(seconds * SR)}
 
 
 def config3(V=1024, seconds=60.0, cmod_pairs=0):
@@ -110,7 +132,7 @@ def config4(V=4096, seconds=30.0, rate_hz=8.0, seed=0x5EED0002):
     setup = []
     for v in range(V):
         setup += pcm_voice(v, V)
-    events = {}
+    timed = []
     rng = XorShift64(seed)
     for v in range(V):
         t = 0.0
@@ -119,16 +141,16 @@ def config4(V=4096, seconds=30.0, rate_hz=8.0, seed=0x5EED0002):
             t += -math.log(1.0 - rng.uniform()) / rate_hz
             if t >= seconds:
                 break
-            k = callback_for_time(t * SR)
             if v % 4 == 0:
-                _add(events, k, ("envelope_velocity", v, 0.0 if held else 1.0))
+                timed.append((int(t * SR), ("envelope_velocity", v, 0.0 if held else 1.0)))
                 held = not held
             else:
-                _add(events, k, ("voice_trigger", v))
+                timed.append((int(t * SR), ("voice_trigger", v)))
     for v in range(V):
-        _add(events, 0, ("voice_trigger", v))
+        setup.append(("voice_trigger", v))        # one-shots are silent until triggered
+    timed.sort(key=lambda x: x[0])
     return {"name": "config4_pcm_retrigger", "voices": V, "tables": {}, "setup": setup,
-            "events": events, "frames": int(seconds * SR)}
+            "timed": timed, "events": bucket(timed), "frames": int(seconds * SR)}
 
 
 def config5(V=65536, seconds=600.0, luts=None, event_seconds=None, seed=0x5EED0005):
@@ -150,24 +172,22 @@ def config5(V=65536, seconds=600.0, luts=None, event_seconds=None, seed=0x5EED00
             c = pcm_voice(u, V)
         # the recipes are written for voice index u: retarget to v, keep amp = 40/V
         setup += [(x[0], v) + tuple(x[2:]) for x in c]
-    events = {}
+    timed = []
     horizon = seconds if event_seconds is None else min(seconds, event_seconds)
     rng = XorShift64(seed)
     for v in range(V):
         t = 10.0 * rng.uniform()
-        first = True
         while t < horizon:
-            k = callback_for_time(t * SR)
             if v % 3 == 2:
-                _add(events, k, ("voice_trigger", v))
+                timed.append((int(t * SR), ("voice_trigger", v)))
             else:
-                _add(events, k, ("envelope_velocity", v, 1.0))
+                timed.append((int(t * SR), ("envelope_velocity", v, 1.0)))
             t += 10.0
-            first = False
         if v % 3 == 2:
-            _add(events, 0, ("voice_trigger", v))     # one-shots start silent until triggered
-    return {"name": "config5_mixed_65536", "voices": V, "tables": tables, "setup": setup,
-            "events": events, "frames": int(seconds * SR)}
+            setup.append(("voice_trigger", v))     # one-shots are silent until triggered
+    timed.sort(key=lambda x: x[0])
+    return {"name": "config5_mixed_%d" % V, "voices": V, "tables": tables, "setup": setup,
+            "timed": timed, "events": bucket(timed), "frames": int(seconds * SR)}
 
 
 def install(api, wl):
