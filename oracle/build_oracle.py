@@ -117,7 +117,9 @@ def build_port(force=False):
         return None
     if not force and newer(out, srcs + [__file__]):
         return out
-    run(["gcc"] + PIN_CFLAGS + ["-shared", "-Wall", "-I" + os.path.join(ROOT, "include"),
+    # -Bsymbolic: the port's own skb_* definitions win even when the CUDA engine
+    # (same ABI, same names) is already loaded RTLD_GLOBAL in the process
+    run(["gcc"] + PIN_CFLAGS + ["-shared", "-Wall", "-Wl,-Bsymbolic", "-I" + os.path.join(ROOT, "include"),
          srcs[0], "-o", out, "-lm"])
     return out
 
@@ -139,7 +141,7 @@ def build_dropin(v, backend, force=False):
         os.makedirs(PORT_OUT, exist_ok=True)
         out = os.path.join(PORT_OUT, "libskred_dropin_port_v%d.so" % v)
         extra_src = [os.path.join(HERE, "skred_port.c")]
-        link = []
+        link = ["-Wl,-Bsymbolic"]
     else:
         os.makedirs(REF_OUT, exist_ok=True)
         out = os.path.join(REF_OUT, "libskred_dropin_cuda_v%d.so" % v)
