@@ -149,6 +149,9 @@ typedef struct skb_config {
 } skb_config;
 
 #define SKB_CFG_DEFAULT 0u
+/* testing aid: render every free voice through the generic per-frame code path
+ * instead of the warp-specialised one (both must produce identical bits) */
+#define SKB_CFG_FORCE_GENERIC 1u
 
 int  skb_create(skb_engine **out, const skb_config *cfg);
 void skb_destroy(skb_engine *e);

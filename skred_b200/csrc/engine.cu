@@ -574,7 +574,8 @@ int skb_render_mix(skb_engine *e, int nframes, uint64_t ssc_before, const float 
     const int grid = (e->n_free_pad + SKB_FREE_THREADS - 1) / SKB_FREE_THREADS;
     k_render_free<<<grid, SKB_FREE_THREADS, 0, st>>>(e->d_pq, e->d_sq[e->cur], e->cap, e->n_free_pad, e->d_tables,
                                                      e->d_noise, nframes, (unsigned long long)ssc_before,
-                                                     e->d_partials, nframes);
+                                                     e->d_partials, nframes,
+                                                     (e->cfg.flags & SKB_CFG_FORCE_GENERIC) ? 1 : 0);
     e->stats.kernel_launches++;
   }
   if (!e->bins.empty()) {

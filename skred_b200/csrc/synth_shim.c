@@ -122,6 +122,7 @@ static skb_engine *engine(void) {
   cfg.max_frames = g_cfg_max_frames;
   cfg.rank = g_cfg_rank;
   cfg.world = g_cfg_world;
+  if ((s = getenv("SKB_FORCE_GENERIC")) && atoi(s)) cfg.flags |= SKB_CFG_FORCE_GENERIC;
   int r = skb_create(&g_engine, &cfg);
   if (r != SKB_OK || !g_engine) {
     fprintf(stderr, "skred_b200: FATAL: cannot create %s engine (error %d); there is no CPU fallback\n",

@@ -97,3 +97,19 @@ def test_big_callbacks_equal_small_callbacks(luts):
     ob = b.render(8192, block=4096)
     assert np.array_equal(oa.view(np.uint32), ob.view(np.uint32))
     assert_state_equal(a.state(), b.state())
+
+
+@pytest.mark.parametrize("name", ["lut_adsr", "korg_cz_filter", "pcm_retrigger", "misc"])
+def test_specialised_path_equals_generic_path(name, luts, monkeypatch):
+    """The warp-specialised fast path and the generic per-frame path of k_render_free
+    must produce identical bits (same ops on the same operands, only hoisted)."""
+    wl = cases.SYNTHETIC[name](luts)
+    a = O.DropinCuda(wl["voices"])
+    cases.drive_setup(a, wl)
+    oa = cases.drive_render(a, wl)
+    monkeypatch.setenv("SKB_FORCE_GENERIC", "1")
+    b = O.DropinCuda(wl["voices"])
+    cases.drive_setup(b, wl)
+    ob = cases.drive_render(b, wl)
+    assert np.array_equal(oa.view(np.uint32), ob.view(np.uint32))
+    assert_state_equal(a.state(), b.state())
