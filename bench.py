@@ -125,19 +125,31 @@ def _ref_worker(args):
         if mine:
             ev[k] = mine
     out = np.zeros((frames_per_step, 2), dtype=np.float32)
-    times = []
+    fin = s.array("voice_finished", C.c_int)
+    amp = s.array("voice_amp")
+
+    def alive():
+        # voices the loop renders (not skipped by synth.c:531-542)
+        return int(np.count_nonzero((fin[:shard] == 0) & (amp[:shard] != 0.0)))
+
+    times, active = [], []
     k = 0
     for step in range(warmup + steps):
-        t0 = time.perf_counter()
+        t_step, a_step = 0.0, 0.0
         done = 0
         while done < frames_per_step:
             if k in ev:
                 s.apply(ev[k])
+            a0 = alive()                       # untimed bookkeeping
+            t0 = time.perf_counter()
             s._synth(out[done:done + 512], 512)
+            t_step += time.perf_counter() - t0
+            a_step += 0.5 * (a0 + alive()) * 512   # a voice that finishes inside the block counts half
             done += 512
             k += 1
-        times.append(time.perf_counter() - t0)
-    return times[warmup:]
+        times.append(t_step)
+        active.append(a_step)
+    return times[warmup:], active[warmup:]
 
 
 def run_reference_cpu(V, frames_per_step, steps, warmup, procs, shard=4096, voices_limit=None):
@@ -154,10 +166,11 @@ def run_reference_cpu(V, frames_per_step, steps, warmup, procs, shard=4096, voic
     # shards run `procs` at a time: step time of the job = sum over waves of the slowest shard
     per_step = np.zeros(steps)
     for w0 in range(0, nshards, procs):
-        per_step += np.max(np.array(res[w0:w0 + procs]), axis=0)
+        per_step += np.max(np.array([r[0] for r in res[w0:w0 + procs]]), axis=0)
     sec = float(np.mean(per_step))
     voices = nshards * shard
-    return voices * frames_per_step / sec, sec, voices, procs, wall
+    active = float(np.mean(np.sum(np.array([r[1] for r in res]), axis=0)))     # rendered voice-frames per step
+    return active / sec, sec, voices, procs, wall, active / (voices * frames_per_step)
 
 
 def reference_arm(a):
@@ -172,13 +185,14 @@ def reference_arm(a):
         return 0
     cores = os.cpu_count() or 1
     frames = 512 if a.ref_frames is None else a.ref_frames          # bounded sample: one callback per step
-    vps, sec, voices, procs, wall = run_reference_cpu(V, frames, a.steps, a.warmup, cores, shard)
+    vps, sec, voices, procs, wall, frac = run_reference_cpu(V, frames, a.steps, a.warmup, cores, shard)
     line = {
         "impl": "reference", "metric": METRIC, "value": vps, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "config5: %d voices mixed LUT/Korg+CZ+biquad/PCM, sparse retrigger events" % V,
-                   "voices": voices, "frames_per_step": frames,
+                   "voices": voices, "frames_per_step": frames, "active_fraction": frac,
+                   "counting": "rendered voice-frames only: voices skipped by synth.c:531-542 (finished one-shots) do not count",
                    "parallelism": "%d independent reference processes x %d voices (reference is single-threaded)" % (procs, shard)},
         "cpu_baseline": {"value": vps, "unit": UNIT, "cores": procs, "kind": "reference",
                          "sample": "%d voices x %d frames per step, %d steps; synth.c compiled gcc -O2 -ffp-contract=off" % (voices, frames, a.steps)},
@@ -270,6 +284,7 @@ def own_arm(a):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    eng.skb_sync(sk.engine, sp)
     s_before = sk.stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern_ms = []
@@ -280,15 +295,20 @@ def own_arm(a):
     e1.record(stream)
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    eng.skb_sync(sk.engine, sp)
     s_after = sk.stats()
     launches = int(s_after.kernel_launches - s_before.kernel_launches) + (a.steps if world > 1 else 0)
 
     # dominant kernel alone (k_render_free + bins + reduce), CUDA events inside the engine
+    kern_active = []
     for _ in range(3):
+        a_b = sk.stats().active_voice_frames
         step_device()
         sk.lib.skb_shim_discard_gain()
         eng.skb_sync(sk.engine, sp)
-        kern_ms.append(sk.stats().last_render_ms)
+        st_k = sk.stats()
+        kern_ms.append(st_k.last_render_ms)
+        kern_active.append((st_k.active_voice_frames - a_b) / (F // LF))      # per launch
     barrier()
     sk.lib.skb_shim_discard_gain()
 
@@ -296,12 +316,14 @@ def own_arm(a):
     for _ in range(a.warmup):
         step_e2e()
     barrier()
+    eng.skb_sync(sk.engine, sp)
     s_b = sk.stats()
     t0 = time.perf_counter()
     for _ in range(a.steps):
         step_e2e()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    eng.skb_sync(sk.engine, sp)
     s_a = sk.stats()
     clk = clocks.stop() if rank == 0 else None
     ops = int(s_a.ops_applied - s_b.ops_applied)
@@ -309,13 +331,31 @@ def own_arm(a):
     h2d = (ops * 32 + par * 132 + a.steps * F * 4) / a.steps
     d2h = F * 8
 
-    value = V * F * a.steps / (dev_ms * 1e-3)
-    e2e = V * F * a.steps / e2e_s
+    def sum_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # rendered voice-frames (voices the loop skips — finished one-shots — do not count)
+    act_dev = sum_over_ranks(s_after.active_voice_frames - s_before.active_voice_frames)
+    act_e2e = sum_over_ranks(s_a.active_voice_frames - s_b.active_voice_frames)
+    value = act_dev / (dev_ms * 1e-3)
+    e2e = act_e2e / e2e_s
     k_ms = float(np.mean(kern_ms))
-    algo_bytes = owned * BYTES_PER_VOICE_LAUNCH + LF * 8
+    k_act = float(np.mean(kern_active))
+    # launch traffic: every owned voice's amp + first state group are read (32 B) to decide the skip;
+    # a rendered voice moves its full 276 B record
+    alive_per_launch = k_act / LF
+    algo_bytes = alive_per_launch * BYTES_PER_VOICE_LAUNCH + (owned - alive_per_launch) * 32.0 + LF * 8
     ach_gbs = algo_bytes / (k_ms * 1e-3) / 1e9
     fp32_peak = N_SM * FP32_LANES_PER_SM * sm_mhz * 1e6
-    ach_flops = owned * LF * FLOPS_PER_VOICE_SAMPLE / (k_ms * 1e-3)
+    # config 5 by v%3: LUT (15 ops) and Korg+CZ+biquad (32 ops) voices always render; the one-shot PCM third (15 ops)
+    # renders only while a sample plays
+    alive_pcm = max(0.0, alive_per_launch - 2.0 * owned / 3.0)
+    flops_vs = (owned / 3.0 * 15.0 + owned / 3.0 * 32.0 + alive_pcm * 15.0) / max(alive_per_launch, 1.0)
+    ach_flops = k_act * flops_vs / (k_ms * 1e-3)
 
     if rank == 0:
         line = {
@@ -324,6 +364,9 @@ def own_arm(a):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "config5: %d voices mixed LUT/Korg+CZ+biquad/PCM, sparse retrigger events" % V,
                        "voices": V, "frames_per_step": F, "frames_per_launch": LF, "block_frames": 512,
+                       "active_fraction": act_dev / (V * F * a.steps),
+                       "counting": "rendered voice-frames only: voices skipped by synth.c:531-542 (finished one-shots) do not count",
+                       "value_counting_all_voice_slots": V * F * a.steps / (dev_ms * 1e-3),
                        "parallelism": "voice-sharded x%d, NCCL reduce of stereo partials" % world if world > 1 else "1 GPU",
                        "l2": "state+params %.1f MB per launch, each word touched once per launch (no reuse to cache)" % (owned * 276 / 1e6)},
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
@@ -332,7 +375,7 @@ def own_arm(a):
                          "note": "the path is FP32-issue bound, not HBM bound (SURVEY 8d): see roofline_fp32"},
             "roofline_fp32": {"bound": "fp32-issue (no FMA: parity mode rounds every op)", "achieved": ach_flops / 1e12,
                               "peak": fp32_peak / 1e12, "unit": "Tflop/s (1 op per lane-issue)",
-                              "frac": ach_flops / fp32_peak, "flops_per_voice_sample": FLOPS_PER_VOICE_SAMPLE},
+                              "frac": ach_flops / fp32_peak, "flops_per_voice_sample": flops_vs},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s / a.steps * 1e3, "api": "synth(buffer, NULL, %d, 2, NULL)" % F},
             "gpu_launches": launches,
@@ -367,7 +410,7 @@ def cpu_baseline(V):
     if not O.have_ref(shard):
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
     frames, steps = 2048, 3
-    vps, sec, voices, procs, wall = run_reference_cpu(V, frames, steps, 1, 1, shard, voices_limit=shard)
+    vps, sec, voices, procs, wall, frac = run_reference_cpu(V, frames, steps, 1, 1, shard, voices_limit=shard)
     return {"value": vps, "unit": UNIT, "cores": 1, "kind": "reference",
             "sample": "first %d voices of the same load x %d frames x %d steps (%.1f s of CPU), synth.c gcc -O2 -ffp-contract=off"
                       % (voices, frames, steps, wall)}

@@ -222,6 +222,8 @@ typedef struct skb_stats {
   int32_t  n_owned_voices;
   float    last_render_ms;    /* device time of the last skb_render_mix (CUDA events) */
   int32_t  _pad;
+  uint64_t active_voice_frames; /* voice-frames actually rendered (not skipped by synth.c:531-542) as of the
+                                   last skb_finish / skb_sync: the numerator of voice-samples/s */
 } skb_stats;
 int  skb_get_stats(skb_engine *e, skb_stats *out);
 

@@ -315,6 +315,7 @@ int skb_render_mix(skb_engine *e, int nframes, uint64_t ssc, const float *noise,
       skb_voice_state *s = &e->st[n];
       if (s->finished) { s->sample = 0.0f; continue; }            /* :531-536 */
       if (p->amp == 0) { s->sample = 0.0f; continue; }            /* :537-542 */
+      e->stats.active_voice_frames++;                             /* rendered, not skipped */
       float f;
       if (p->flags & SKB_F_NOISE) {                               /* :543-546 */
         f = white;

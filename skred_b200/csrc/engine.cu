@@ -58,7 +58,8 @@ struct skb_engine {
   std::vector<int32_t> bin_of_voice;                /* -1 = free */
   std::vector<skb_bin_desc> bins;
   std::vector<uint64_t> edge_sig;                   /* per voice: hash of its live edges (re-plan trigger) */
-  int n_free = 0, n_free_pad = 0, n_slots = 0, n_rows = 0, n_free_rows = 0, max_bin_threads = 0;
+  int n_free = 0, n_free_pad = 0, n_slots = 0, n_free_rows = 0, max_bin_threads = 0;
+  int n_sm = 148, free_ctas = 0, free_groups = 0, n_groups = 0;   /* partial rows come in groups of SKB_CTA_WARPS */
 
   /* device */
   float4 *d_pq = nullptr, *d_sq[2] = {nullptr, nullptr};
@@ -68,6 +69,10 @@ struct skb_engine {
   std::vector<TableDesc> tables;
   skb_bin_desc *d_bins = nullptr; int d_bins_cap = 0;
   float2 *d_partials = nullptr; size_t partials_cap = 0;
+  int *d_rowcount = nullptr; size_t rowcount_cap = 0;
+  float2 *d_part2 = nullptr;
+  unsigned int *d_tickets = nullptr;
+  unsigned long long *d_counters = nullptr, *h_counters = nullptr;
   float2 *d_mix = nullptr, *d_out = nullptr;
   float *d_gain = nullptr, *d_noise = nullptr;
   int *d_idx = nullptr; size_t d_idx_cap = 0;       /* slots / old_slot scratch */
@@ -146,6 +151,7 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
   e->cfg = *cfg;
   if (e->cfg.max_frames < 512) e->cfg.max_frames = 512;
   e->n = cfg->n_voices;
+  e->n_sm = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
   memset(&e->stats, 0, sizeof(e->stats));
   const int n = e->n, mf = e->cfg.max_frames;
   e->cap = ((n + 31) / 32) * 32 + 64;
@@ -170,6 +176,14 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
             cudaMalloc((void **)&e->d_out, (size_t)mf * sizeof(float2)) == cudaSuccess &&
             cudaMalloc((void **)&e->d_gain, (size_t)mf * sizeof(float)) == cudaSuccess &&
             cudaMalloc((void **)&e->d_noise, (size_t)mf * sizeof(float)) == cudaSuccess &&
+            cudaMalloc((void **)&e->d_part2, (size_t)SKB_RED_CHUNKS * mf * sizeof(float2)) == cudaSuccess &&
+            cudaMalloc((void **)&e->d_tickets, (size_t)(mf / SKB_RED_X + 1) * sizeof(unsigned int)) == cudaSuccess &&
+            cudaMalloc((void **)&e->d_counters, 2 * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMallocHost((void **)&e->h_counters, 2 * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMemset(e->d_tickets, 0, (size_t)(mf / SKB_RED_X + 1) * sizeof(unsigned int)) == cudaSuccess &&
+            cudaMemset(e->d_counters, 0, 2 * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaFuncSetAttribute(k_render_free, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(SKB_CTA_WARPS * SKB_TILE_FLOAT2 * sizeof(float2))) == cudaSuccess &&
             cudaMallocHost((void **)&e->h_gain, (size_t)mf * sizeof(float)) == cudaSuccess &&
             cudaMallocHost((void **)&e->h_noise, (size_t)mf * sizeof(float)) == cudaSuccess &&
             cudaMallocHost((void **)&e->h_out, (size_t)mf * sizeof(float2)) == cudaSuccess &&
@@ -198,6 +212,8 @@ void skb_destroy(skb_engine *e) {
   cudaFree(e->d_bins); cudaFree(e->d_partials); cudaFree(e->d_mix); cudaFree(e->d_out);
   cudaFree(e->d_gain); cudaFree(e->d_noise); cudaFree(e->d_idx); cudaFree(e->d_recs);
   cudaFree(e->d_ops); cudaFree(e->d_runs); cudaFree(e->d_snap);
+  cudaFree(e->d_rowcount); cudaFree(e->d_part2); cudaFree(e->d_tickets); cudaFree(e->d_counters);
+  cudaFreeHost(e->h_counters);
   cudaFreeHost(e->h_gain); cudaFreeHost(e->h_noise); cudaFreeHost(e->h_out); cudaFreeHost(e->h_idx);
   cudaFreeHost(e->h_recs); cudaFreeHost(e->h_ops); cudaFreeHost(e->h_runs); cudaFreeHost(e->h_snap);
   if (e->ev_h2d) cudaEventDestroy(e->ev_h2d);
@@ -262,14 +278,19 @@ static uint64_t edge_signature(const skb_voice_params *p, int v, int n) {
 static uint64_t feature_key(const skb_voice_params *p) {
   uint64_t k = 0;
   const bool silent = (p->amp == 0.0f);
-  k |= (uint64_t)(silent ? 1 : 0) << 40;
+  /* voices that need the generic per-frame code keep to their own warps */
+  const bool generic = (p->flags & (SKB_F_NOISE | SKB_F_REVERSE | SKB_F_DISCONNECT)) || !(p->flags & SKB_F_SMOOTHER) ||
+                       p->sample_hold_max != 0 || p->quantize != 0 || p->amp_mod_osc >= 0 || p->pan_mod_osc >= 0 ||
+                       ((p->flags & SKB_F_LOOP_ENABLED) && (p->flags & SKB_F_LOOP_VALID));
+  k |= (uint64_t)(generic ? 1 : 0) << 42;
+  k |= (uint64_t)(silent ? 1 : 0) << 41;
+  k |= (uint64_t)((p->flags & SKB_F_ONE_SHOT) ? 1 : 0) << 40;
   k |= (uint64_t)((p->flags & SKB_F_NOISE) ? 1 : 0) << 39;
   k |= (uint64_t)(p->cz_mode & 7) << 36;
   k |= (uint64_t)(p->filter_mode ? 1 : 0) << 35;
   k |= (uint64_t)((p->flags & SKB_F_USE_ENV) ? 1 : 0) << 34;
   k |= (uint64_t)(p->quantize ? 1 : 0) << 33;
   k |= (uint64_t)(p->sample_hold_max ? 1 : 0) << 32;
-  k |= (uint64_t)((p->flags & SKB_F_ONE_SHOT) ? 1 : 0) << 31;
   k |= (uint64_t)((uint32_t)(p->table_id + 1) & 0x7fffffffu);
   return k;
 }
@@ -375,11 +396,15 @@ static int replan(skb_engine *e, cudaStream_t st) {
   }
   int slot = e->n_free_pad;
   e->n_free_rows = e->n_free_pad / 32;
+  /* partial-row groups: one per (CTA, batch) of k_render_free, then the bins 16 to a group */
+  e->free_ctas = std::min(e->n_sm, e->n_free_rows);
+  e->free_groups = e->free_ctas ? e->free_ctas * (((e->n_free_rows + e->free_ctas - 1) / e->free_ctas + SKB_CTA_WARPS - 1) / SKB_CTA_WARPS) : 0;
+  e->n_groups = e->free_groups + ((int)binv.size() + SKB_CTA_WARPS - 1) / SKB_CTA_WARPS;
   e->max_bin_threads = 0;
   for (size_t b = 0; b < binv.size(); b++) {
     std::sort(binv[b].begin(), binv[b].end());
     skb_bin_desc d;
-    d.slot0 = slot; d.size = (int)binv[b].size(); d.nlevels = 1; d.row = e->n_free_rows + (int)b;
+    d.slot0 = slot; d.size = (int)binv[b].size(); d.nlevels = 1; d.row = e->free_groups * SKB_CTA_WARPS + (int)b;
     for (int i = 0; i < d.size; i++) {
       const int v = binv[b][i];
       e->slot_of_voice[v] = slot + i;
@@ -397,7 +422,6 @@ static int replan(skb_engine *e, cudaStream_t st) {
     slot += d.size;
   }
   e->n_slots = slot;
-  e->n_rows = e->n_free_rows + (int)e->bins.size();
   if (e->n_slots > e->cap) return fail(e, SKB_ERR_CAPACITY, "slot capacity exceeded");
   for (int v = 0; v < n; v++) e->edge_sig[v] = edge_signature(&e->par[v], v, n);
 
@@ -428,6 +452,15 @@ static int replan(skb_engine *e, cudaStream_t st) {
     }
     /* pageable source: synchronous with respect to the host, ordered on st */
     CK(cudaMemcpyAsync(e->d_bins, e->bins.data(), e->bins.size() * sizeof(skb_bin_desc), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  {
+    /* rowcount: free groups are written by k_render_free each launch (0 until then), bin groups are static */
+    cudaError_t rr = grow_dev(&e->d_rowcount, &e->rowcount_cap, (size_t)std::max(e->n_groups, 1));
+    if (rr != cudaSuccess) return fail(e, SKB_ERR_CUDA, "rowcount alloc", cudaGetErrorString(rr));
+    std::vector<int> rc((size_t)std::max(e->n_groups, 1), 0);
+    for (size_t b = 0; b < e->bins.size(); b++) rc[(size_t)e->free_groups + b / SKB_CTA_WARPS]++;
+    CK(cudaMemcpyAsync(e->d_rowcount, rc.data(), rc.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
   }
   /* every owned voice gets a fresh record */
@@ -563,19 +596,19 @@ int skb_render_mix(skb_engine *e, int nframes, uint64_t ssc_before, const float 
     CK(cudaMemcpyAsync(e->d_noise, e->h_noise, (size_t)nframes * sizeof(float), cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(e->ev_h2d, st));
   }
-  const size_t need = (size_t)std::max(e->n_rows, 1) * (size_t)nframes;
-  if (need > e->partials_cap) {
+  const size_t n_prow = (size_t)std::max(e->n_groups, 1) * SKB_CTA_WARPS;
+  if (n_prow * (size_t)e->cfg.max_frames > e->partials_cap) {
     CK(cudaStreamSynchronize(st));
-    cudaError_t r = grow_dev(&e->d_partials, &e->partials_cap, (size_t)std::max(e->n_rows, 1) * (size_t)e->cfg.max_frames);
+    cudaError_t r = grow_dev(&e->d_partials, &e->partials_cap, n_prow * (size_t)e->cfg.max_frames);
     if (r != cudaSuccess) return fail(e, SKB_ERR_CUDA, "partials alloc", cudaGetErrorString(r));
   }
   CK(cudaEventRecord(e->ev_t0, st));
-  if (e->n_free_pad > 0) {
-    const int grid = (e->n_free_pad + SKB_FREE_THREADS - 1) / SKB_FREE_THREADS;
-    k_render_free<<<grid, SKB_FREE_THREADS, 0, st>>>(e->d_pq, e->d_sq[e->cur], e->cap, e->n_free_pad, e->d_tables,
-                                                     e->d_noise, nframes, (unsigned long long)ssc_before,
-                                                     e->d_partials, nframes,
-                                                     (e->cfg.flags & SKB_CFG_FORCE_GENERIC) ? 1 : 0);
+  if (e->n_free_rows > 0) {
+    const size_t smem = (size_t)SKB_CTA_WARPS * SKB_TILE_FLOAT2 * sizeof(float2);
+    k_render_free<<<e->free_ctas, SKB_CTA_THREADS, smem, st>>>(e->d_pq, e->d_sq[e->cur], e->cap, e->n_free_rows, e->n_free,
+                                                               e->d_tables, e->d_noise, nframes, (unsigned long long)ssc_before,
+                                                               e->d_partials, nframes, e->d_rowcount, e->d_counters,
+                                                               (e->cfg.flags & SKB_CFG_FORCE_GENERIC) ? 1 : 0);
     e->stats.kernel_launches++;
   }
   if (!e->bins.empty()) {
@@ -583,13 +616,14 @@ int skb_render_mix(skb_engine *e, int nframes, uint64_t ssc_before, const float 
     const size_t smem = (size_t)3 * nt * sizeof(float) + (size_t)2 * (nt / 32) * sizeof(float2);
     k_render_bins<<<(int)e->bins.size(), nt, smem, st>>>(e->d_pq, e->d_sq[e->cur], e->cap, e->d_bins, e->d_tables,
                                                          e->d_noise, nframes, (unsigned long long)ssc_before,
-                                                         e->d_partials, nframes);
+                                                         e->d_partials, nframes, e->d_counters + 1);
     e->stats.kernel_launches++;
   }
-  if (e->n_rows > 0) {
+  if (e->n_groups > 0) {
     dim3 blk(SKB_RED_X, SKB_RED_Y);
-    k_reduce_rows<<<(nframes + SKB_RED_X - 1) / SKB_RED_X, blk, 0, st>>>(e->d_partials, e->n_rows, nframes, nframes,
-                                                                           (float2 *)d_mix);
+    dim3 grd((nframes + SKB_RED_X - 1) / SKB_RED_X, std::max(1, std::min(SKB_RED_CHUNKS, e->n_groups / 2)));
+    k_reduce_rows<<<grd, blk, 0, st>>>(e->d_partials, e->d_rowcount, e->n_groups, nframes, nframes, e->d_part2,
+                                       e->d_tickets, (float2 *)d_mix);
     e->stats.kernel_launches++;
   } else {
     CK(cudaMemsetAsync(d_mix, 0, (size_t)nframes * sizeof(float2), st));
@@ -617,7 +651,9 @@ int skb_finish(skb_engine *e, const float *d_mix, int nframes, const float *gain
   k_finish<<<(nframes + 255) / 256, 256, 0, st>>>((const float2 *)d_mix, e->d_gain, e->d_out, nframes);
   e->stats.kernel_launches++;
   CK(cudaMemcpyAsync(e->h_out, e->d_out, (size_t)nframes * sizeof(float2), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(e->h_counters, e->d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  e->stats.active_voice_frames = e->h_counters[0] + e->h_counters[1];
   if (num_channels == 2) {
     memcpy(out, e->h_out, (size_t)nframes * sizeof(float2));
   } else {
@@ -655,7 +691,10 @@ int skb_render(skb_engine *e, int nframes, uint64_t ssc_before, const float *gai
 int skb_sync(skb_engine *e, void *stream) {
   if (!e) return SKB_ERR_ARG;
   cudaSetDevice(e->cfg.device);
+  CK(cudaMemcpyAsync(e->h_counters, e->d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                     stream ? (cudaStream_t)stream : e->stream));
   CK(cudaStreamSynchronize(stream ? (cudaStream_t)stream : e->stream));
+  e->stats.active_voice_frames = e->h_counters[0] + e->h_counters[1];
   if (e->timing_pending) {
     float ms = 0.0f;
     if (cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1) == cudaSuccess) e->stats.last_render_ms = ms;

@@ -50,6 +50,7 @@ struct VoiceS {
   float y2; int env_active; float env_vel, sm_gain;
   float panL, panR; unsigned long long env_start;
   unsigned long long env_rel;
+  int nact;                  /* frames actually rendered (not skipped) in this launch; not stored */
 };
 
 __device__ __forceinline__ float4 ldq(const float4 *base, int k, int cap, int slot) {
@@ -77,6 +78,7 @@ __device__ __forceinline__ void load_state(const float4 *__restrict__ q, int cap
   s.env_start = ((unsigned long long)__float_as_uint(a.w) << 32) | __float_as_uint(a.z);
   a = ldq(q, 4, cap, slot);
   s.env_rel = ((unsigned long long)__float_as_uint(a.y) << 32) | __float_as_uint(a.x);
+  s.nact = 0;
 }
 
 __device__ __forceinline__ void store_state(float4 *__restrict__ q, int cap, int slot, const VoiceS &s) {
@@ -225,6 +227,7 @@ __device__ __forceinline__ float2 voice_frame(const VoiceP &p, const VoiceK &k, 
                                               const float *__restrict__ tables, const Mod &mod) {
   if (s.finished) { s.sample = 0.0f; return make_float2(0.0f, 0.0f); }          /* :531-536 */
   if (p.amp == 0.0f) { s.sample = 0.0f; return make_float2(0.0f, 0.0f); }       /* :537-542 */
+  s.nact++;
   float f;
   if (p.flags & SKB_F_NOISE) {                                                    /* :543-546 */
     f = white;
@@ -509,6 +512,7 @@ __device__ __forceinline__ void render_fast(const VoiceP &p, const VoiceK &k, Vo
         }
         s.sm_gain = g;
         s.sample = last;
+        s.nact += SKB_SUB;
       }
 #pragma unroll
       for (int j = 0; j < SKB_SUB; j++) mytile[(sb + j) * SKB_TILE_STRIDE + lane] = make_float2(L[j], R[j]);
@@ -543,59 +547,100 @@ __device__ __forceinline__ bool lane_needs_generic(const VoiceP &p, const VoiceS
   return false;
 }
 
-__global__ void __launch_bounds__(SKB_FREE_THREADS)
-k_render_free(const float4 *__restrict__ pq, float4 *__restrict__ sq, int cap, int n_slots,
+/* Persistent form: ONE CTA per SM (grid = min(#SM, rows)), SKB_CTA_WARPS warps.  The free
+ * range is cut into ROWS of 32 consecutive slots (slots are sorted by feature key, so a row
+ * is homogeneous); row r belongs to CTA r % gridDim.x, which deals every feature class
+ * evenly over the SMs.  A CTA takes its rows in BATCHES of SKB_CTA_WARPS and first
+ * COMPACTS the batch: voices that are skipped for the whole launch (finished one-shots,
+ * amp == 0; synth.c:531-542 — state edits only happen at launch boundaries) are dropped
+ * and the live ones are packed, in slot order, into as few warps as possible.  Each live
+ * warp writes one partial row; rowcount[group] tells k_reduce_rows how many. */
+#define SKB_CTA_WARPS 16
+#define SKB_CTA_THREADS (SKB_CTA_WARPS * 32)
+#define SKB_TILE_FLOAT2 (SKB_CHUNK * SKB_TILE_STRIDE)
+
+__global__ void __launch_bounds__(SKB_CTA_THREADS, 1)
+k_render_free(const float4 *__restrict__ pq, float4 *__restrict__ sq, int cap, int n_rows, int n_free,
               const float *__restrict__ tables, const float *__restrict__ noise,
               int nframes, unsigned long long ssc_before,
-              float2 *__restrict__ partials, int row_stride, int force_generic) {
-  __shared__ float2 tile[SKB_FREE_THREADS / 32][SKB_CHUNK * SKB_TILE_STRIDE];
+              float2 *__restrict__ partials, int row_stride, int *__restrict__ rowcount,
+              unsigned long long *__restrict__ counters, int force_generic) {
+  extern __shared__ float2 tile_all[];           /* [SKB_CTA_WARPS][SKB_CHUNK * SKB_TILE_STRIDE] */
+  __shared__ int s_cnt[SKB_CTA_WARPS];
+  __shared__ int s_list[SKB_CTA_THREADS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int slot = blockIdx.x * SKB_FREE_THREADS + threadIdx.x;
-  const int row = blockIdx.x * (SKB_FREE_THREADS / 32) + warp;
-  if ((slot & ~31) >= n_slots) return;           /* whole warp beyond the free range */
-  VoiceP p; VoiceS s; VoiceK k;
-  load_params(pq, cap, slot, p);
-  load_state(sq, cap, slot, s);
-  derive_consts(p, k);
-  float2 *mytile = tile[warp];
-  float2 *out_row = partials + (size_t)row * row_stride;
-  /* a voice that is finished or silent now stays so for the whole launch: state
-   * edits only happen at launch boundaries (synth.c:531-542) */
-  const bool dead = s.finished || p.amp == 0.0f;
-  if (__all_sync(0xffffffffu, dead)) {
-    for (int f = lane; f < nframes; f += 32) out_row[f] = make_float2(0.0f, 0.0f);
-    if (s.sample != 0.0f) { s.sample = 0.0f; store_state(sq, cap, slot, s); }
-    return;
-  }
-  const bool generic = force_generic || __any_sync(0xffffffffu, lane_needs_generic(p, s, nframes, ssc_before));
-  int done = 0;
-  if (!generic) {
-    done = nframes & ~(SKB_CHUNK - 1);
-    render_fast(p, k, s, tables, done, ssc_before, mytile, out_row, lane);
-  }
-  /* generic path: everything for a warp with uncommon features, the ragged tail otherwise */
-  const bool wants_noise = (p.flags & SKB_F_NOISE) != 0;
-  const NoMods nomods;
-  for (int base = done; base < nframes; base += SKB_CHUNK) {
-    const int cnt = min(SKB_CHUNK, nframes - base);
-    for (int f = 0; f < cnt; f++) {
-      const float white = wants_noise ? __ldg(noise + base + f) : 0.0f;
-      const float2 o = voice_frame<false>(p, k, s, ssc_before + (unsigned long long)(base + f + 1), white, tables, nomods);
-      mytile[f * SKB_TILE_STRIDE + lane] = o;
+  const int ncta = gridDim.x, cta = blockIdx.x;
+  const int rows_mine = (n_rows - cta + ncta - 1) / ncta;
+  float2 *mytile = tile_all + warp * SKB_TILE_FLOAT2;
+  for (int k0 = 0; k0 < rows_mine; k0 += SKB_CTA_WARPS) {
+    /* ---- compaction of this batch ---- */
+    const int k = k0 + warp;
+    const int cand = (cta + ncta * k) * 32 + lane;
+    bool alive = false;
+    if (k < rows_mine && cand < n_free) {
+      float4 s0 = sq[cand];                                        /* phase, finished, sample, sh_hold */
+      const float amp = pq[cand].x;
+      alive = (__float_as_int(s0.y) == 0) && (amp != 0.0f);
+      if (!alive && s0.z != 0.0f) { s0.z = 0.0f; sq[cand] = s0; }  /* skipped voice: voice_sample = 0 */
     }
-    __syncwarp();
-    if (lane < cnt) {
-      float L = 0.0f, R = 0.0f;
+    const unsigned bal = __ballot_sync(0xffffffffu, alive);
+    if (lane == 0) s_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
 #pragma unroll
-      for (int v = 0; v < 32; v++) {
-        const float2 c = mytile[lane * SKB_TILE_STRIDE + v];
-        L += c.x; R += c.y;
+    for (int i = 0; i < SKB_CTA_WARPS; i++) { const int c = s_cnt[i]; if (i < warp) before += c; total += c; }
+    if (alive) s_list[before + __popc(bal & ((1u << lane) - 1u))] = cand;
+    __syncthreads();
+    const int group = (k0 / SKB_CTA_WARPS) * ncta + cta;
+    const int live_warps = (total + 31) >> 5;
+    if (threadIdx.x == 0) rowcount[group] = live_warps;
+    if (warp < live_warps) {
+      const bool live = (int)threadIdx.x < total;
+      const int slot = live ? s_list[threadIdx.x] : 0;
+      VoiceP p; VoiceS s; VoiceK kk;
+      load_params(pq, cap, slot, p);
+      load_state(sq, cap, slot, s);
+      if (!live) { p.amp = 0.0f; p.flags = SKB_F_SMOOTHER; p.sh_max = 0; p.quant = 0; p.cz_mode = 0;
+                   p.am_ref = SKB_REF_NONE; p.pm_ref = SKB_REF_NONE; p.toff = 0; p.tsize = 1; }   /* padding lane: silent */
+      derive_consts(p, kk);
+      float2 *out_row = partials + (size_t)(group * SKB_CTA_WARPS + warp) * row_stride;
+      const bool generic = force_generic || __any_sync(0xffffffffu, lane_needs_generic(p, s, nframes, ssc_before));
+      int done = 0;
+      if (!generic) {
+        done = nframes & ~(SKB_CHUNK - 1);
+        render_fast(p, kk, s, tables, done, ssc_before, mytile, out_row, lane);
       }
-      out_row[base + lane] = make_float2(L, R);
+      /* generic path: everything for a warp with uncommon features, the ragged tail otherwise */
+      const bool wants_noise = (p.flags & SKB_F_NOISE) != 0;
+      const NoMods nomods;
+      for (int base = done; base < nframes; base += SKB_CHUNK) {
+        const int cnt = min(SKB_CHUNK, nframes - base);
+        for (int f = 0; f < cnt; f++) {
+          const float white = wants_noise ? __ldg(noise + base + f) : 0.0f;
+          const float2 o = voice_frame<false>(p, kk, s, ssc_before + (unsigned long long)(base + f + 1), white, tables, nomods);
+          mytile[f * SKB_TILE_STRIDE + lane] = o;
+        }
+        __syncwarp();
+        if (lane < cnt) {
+          float L = 0.0f, R = 0.0f;
+#pragma unroll
+          for (int v = 0; v < 32; v++) {
+            const float2 c = mytile[lane * SKB_TILE_STRIDE + v];
+            L += c.x; R += c.y;
+          }
+          out_row[base + lane] = make_float2(L, R);
+        }
+        __syncwarp();
+      }
+      if (live) store_state(sq, cap, slot, s);
+      /* rendered (not skipped) voice-frames of this launch: the metric's numerator */
+      int na = live ? s.nact : 0;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) na += __shfl_xor_sync(0xffffffffu, na, d);
+      if (lane == 0 && na) atomicAdd(counters, (unsigned long long)na);
     }
-    __syncwarp();
+    __syncthreads();          /* s_cnt / s_list are reused by the next batch */
   }
-  store_state(sq, cap, slot, s);
 }
 
 /* ======================================================================== */
@@ -624,7 +669,7 @@ k_render_bins(const float4 *__restrict__ pq, float4 *__restrict__ sq, int cap,
               const skb_bin_desc *__restrict__ bins,
               const float *__restrict__ tables, const float *__restrict__ noise,
               int nframes, unsigned long long ssc_before,
-              float2 *__restrict__ partials, int row_stride) {
+              float2 *__restrict__ partials, int row_stride, unsigned long long *__restrict__ counter) {
   extern __shared__ float bsm[];
   const skb_bin_desc bd = bins[blockIdx.x];
   const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
@@ -679,30 +724,65 @@ k_render_bins(const float4 *__restrict__ pq, float4 *__restrict__ sq, int cap,
     out_row[nframes - 1] = make_float2(L, R);
   }
   if (live) store_state(sq, cap, slot, s);
+  int na = live ? s.nact : 0;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) na += __shfl_xor_sync(0xffffffffu, na, d);
+  if (lane == 0 && na) atomicAdd(counter, (unsigned long long)na);
 }
 
 /* ======================================================================== */
 /* K4  reduce_rows: partial rows -> raw stereo mix, fixed order              */
 /* ======================================================================== */
-#define SKB_RED_X 64
+/* Rows come in GROUPS of SKB_CTA_WARPS (one group per CTA batch of k_render_free, then the
+ * modulation bins packed 16 to a group); rowcount[g] of them are valid.  Grid = frame tiles
+ * of 32 x SKB_RED_CHUNKS group chunks, so that ~600 CTAs share the 8 B x rows x frames of
+ * traffic instead of a handful.  Chunk c sums its groups in index order (y-strided, then
+ * the 8 y partials in order) into part2[c][f]; the LAST chunk CTA of a frame tile to
+ * arrive (atomic ticket) adds the chunk partials in chunk order — the result does not
+ * depend on which CTA that is, so the sum is run-to-run deterministic. */
+#define SKB_RED_X 32
 #define SKB_RED_Y 8
+#define SKB_RED_CHUNKS 32
 __global__ void __launch_bounds__(SKB_RED_X * SKB_RED_Y)
-k_reduce_rows(const float2 *__restrict__ partials, int rows, int nframes, int row_stride,
+k_reduce_rows(const float2 *__restrict__ partials, const int *__restrict__ rowcount, int ngroups,
+              int nframes, int row_stride, float2 *__restrict__ part2, unsigned int *__restrict__ tickets,
               float2 *__restrict__ mix) {
   __shared__ float2 acc[SKB_RED_Y][SKB_RED_X];
+  __shared__ unsigned int s_ticket;
   const int f = blockIdx.x * SKB_RED_X + threadIdx.x;
+  const int nch = gridDim.y, c = blockIdx.y;
+  const int per = (ngroups + nch - 1) / nch;
+  const int g0 = c * per, g1 = min(ngroups, g0 + per);
   float L = 0.0f, R = 0.0f;
   if (f < nframes)
-    for (int r = threadIdx.y; r < rows; r += SKB_RED_Y) {
-      const float2 c = partials[(size_t)r * row_stride + f];
-      L += c.x; R += c.y;
+    for (int g = g0; g < g1; g++) {
+      const int nr = rowcount[g];
+      for (int r = threadIdx.y; r < nr; r += SKB_RED_Y) {
+        const float2 v = partials[(size_t)(g * SKB_CTA_WARPS + r) * row_stride + f];
+        L += v.x; R += v.y;
+      }
     }
   acc[threadIdx.y][threadIdx.x] = make_float2(L, R);
   __syncthreads();
-  if (threadIdx.y == 0 && f < nframes) {
+  if (threadIdx.y == 0) {
     for (int y = 1; y < SKB_RED_Y; y++) { L += acc[y][threadIdx.x].x; R += acc[y][threadIdx.x].y; }
-    mix[f] = make_float2(L, R);
+    if (f < nframes) part2[(size_t)c * row_stride + f] = make_float2(L, R);
+    __threadfence();
   }
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) s_ticket = atomicAdd(&tickets[blockIdx.x], 1u);
+  __syncthreads();
+  if (s_ticket != (unsigned)(nch - 1)) return;
+  __threadfence();
+  if (threadIdx.y == 0 && f < nframes) {
+    float l = 0.0f, r = 0.0f;
+    for (int i = 0; i < nch; i++) {
+      const float2 v = __ldcg(&part2[(size_t)i * row_stride + f]);
+      l += v.x; r += v.y;
+    }
+    mix[f] = make_float2(l, r);
+  }
+  if (threadIdx.x == 0 && threadIdx.y == 0) tickets[blockIdx.x] = 0u;     /* ready for the next launch */
 }
 
 /* K5  master volume (synth.c:619-624): the one-pole trace `gain` is computed

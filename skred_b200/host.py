@@ -80,7 +80,8 @@ class skb_stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("frames_rendered", C.c_uint64),
                 ("ops_applied", C.c_uint64), ("params_uploaded", C.c_uint64), ("replans", C.c_uint64),
                 ("n_free_voices", C.c_int32), ("n_group_voices", C.c_int32), ("n_groups", C.c_int32),
-                ("n_owned_voices", C.c_int32), ("last_render_ms", C.c_float), ("_pad", C.c_int32)]
+                ("n_owned_voices", C.c_int32), ("last_render_ms", C.c_float), ("_pad", C.c_int32),
+                ("active_voice_frames", C.c_uint64)]
 
 
 class SynthAPI:
