@@ -41,6 +41,9 @@ int  skb_shim_last_error(void);
  * (synth.c:663-808) and voice_copy (synth.c:1044-1046) keep working. */
 void skb_shim_snapshot(void);
 int  skb_shim_snapshot_range(int first, int n);
+/* Host arrays -> device, same fields (checkpoint resume, or a harness that wrote
+ * voice_phase[] / voice_finished[] directly). */
+int  skb_shim_restore_range(int first, int n);
 
 /* wire.c writes some arrays directly, bypassing the setters (wire.c:639-708:
  * `h`, `s`, `J`, …).  With VOICE_MAX <= 4096 the shim diffs every voice

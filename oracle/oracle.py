@@ -51,6 +51,7 @@ class HarnessSkred(SynthAPI):
         lib.ref_get_filter.argtypes = [C.c_int, C.c_void_p]
         lib.ref_get_envelope.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         self.run_seq = 1 if run_seq else 0
+        self.backend = "ref" if "libskred_ref" in path else ("port" if "dropin_port" in path else "cuda")
         self.cpu_seconds = 0.0
         lib.ref_init()
 
@@ -69,6 +70,17 @@ class HarnessSkred(SynthAPI):
 
     def sync_state(self):
         self.lib.ref_sync_state()
+
+    def engine_stats(self):
+        """skb_stats of the engine behind a drop-in build (port: linked in; cuda: libskred_b200.so)."""
+        from skred_b200.host import skb_stats
+        self.lib.skb_shim_engine.restype = C.c_void_p
+        eng = self.lib.skb_shim_engine()
+        owner = self.lib if self.backend == "port" else load_engine_lib()
+        owner.skb_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+        st = skb_stats()
+        owner.skb_get_stats(eng, C.byref(st))
+        return st
 
     def state(self):
         """Evolving per-voice state as a dict of arrays."""

@@ -70,6 +70,7 @@ struct skb_engine {
   skb_bin_desc *d_bins = nullptr; int d_bins_cap = 0;
   float2 *d_partials = nullptr; size_t partials_cap = 0;
   int *d_rowcount = nullptr; size_t rowcount_cap = 0;
+  float *d_envbuf = nullptr; size_t envbuf_cap = 0;   /* envelope pre-pass rows: [CTA][thread][SKB_ENV_WIN] */
   float2 *d_part2 = nullptr;
   unsigned int *d_tickets = nullptr;
   unsigned long long *d_counters = nullptr, *h_counters = nullptr;
@@ -183,7 +184,7 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
             cudaMemset(e->d_tickets, 0, (size_t)(mf / SKB_RED_X + 1) * sizeof(unsigned int)) == cudaSuccess &&
             cudaMemset(e->d_counters, 0, 2 * sizeof(unsigned long long)) == cudaSuccess &&
             cudaFuncSetAttribute(k_render_free, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(SKB_CTA_WARPS * SKB_TILE_FLOAT2 * sizeof(float2))) == cudaSuccess &&
+                                 (int)skb_free_smem_bytes()) == cudaSuccess &&
             cudaMallocHost((void **)&e->h_gain, (size_t)mf * sizeof(float)) == cudaSuccess &&
             cudaMallocHost((void **)&e->h_noise, (size_t)mf * sizeof(float)) == cudaSuccess &&
             cudaMallocHost((void **)&e->h_out, (size_t)mf * sizeof(float2)) == cudaSuccess &&
@@ -212,6 +213,7 @@ void skb_destroy(skb_engine *e) {
   cudaFree(e->d_bins); cudaFree(e->d_partials); cudaFree(e->d_mix); cudaFree(e->d_out);
   cudaFree(e->d_gain); cudaFree(e->d_noise); cudaFree(e->d_idx); cudaFree(e->d_recs);
   cudaFree(e->d_ops); cudaFree(e->d_runs); cudaFree(e->d_snap);
+  cudaFree(e->d_envbuf);
   cudaFree(e->d_rowcount); cudaFree(e->d_part2); cudaFree(e->d_tickets); cudaFree(e->d_counters);
   cudaFreeHost(e->h_counters);
   cudaFreeHost(e->h_gain); cudaFreeHost(e->h_noise); cudaFreeHost(e->h_out); cudaFreeHost(e->h_idx);
@@ -458,6 +460,8 @@ static int replan(skb_engine *e, cudaStream_t st) {
     /* rowcount: free groups are written by k_render_free each launch (0 until then), bin groups are static */
     cudaError_t rr = grow_dev(&e->d_rowcount, &e->rowcount_cap, (size_t)std::max(e->n_groups, 1));
     if (rr != cudaSuccess) return fail(e, SKB_ERR_CUDA, "rowcount alloc", cudaGetErrorString(rr));
+    rr = grow_dev(&e->d_envbuf, &e->envbuf_cap, (size_t)std::max(e->free_ctas, 1) * SKB_CTA_THREADS * SKB_ENV_WIN);
+    if (rr != cudaSuccess) return fail(e, SKB_ERR_CUDA, "envelope scratch alloc", cudaGetErrorString(rr));
     std::vector<int> rc((size_t)std::max(e->n_groups, 1), 0);
     for (size_t b = 0; b < e->bins.size(); b++) rc[(size_t)e->free_groups + b / SKB_CTA_WARPS]++;
     CK(cudaMemcpyAsync(e->d_rowcount, rc.data(), rc.size() * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -604,10 +608,10 @@ int skb_render_mix(skb_engine *e, int nframes, uint64_t ssc_before, const float 
   }
   CK(cudaEventRecord(e->ev_t0, st));
   if (e->n_free_rows > 0) {
-    const size_t smem = (size_t)SKB_CTA_WARPS * SKB_TILE_FLOAT2 * sizeof(float2);
-    k_render_free<<<e->free_ctas, SKB_CTA_THREADS, smem, st>>>(e->d_pq, e->d_sq[e->cur], e->cap, e->n_free_rows, e->n_free,
+    k_render_free<<<e->free_ctas, SKB_CTA_THREADS, skb_free_smem_bytes(), st>>>(
+                                                               e->d_pq, e->d_sq[e->cur], e->cap, e->n_free_rows, e->n_free,
                                                                e->d_tables, e->d_noise, nframes, (unsigned long long)ssc_before,
-                                                               e->d_partials, nframes, e->d_rowcount, e->d_counters,
+                                                               e->d_partials, nframes, e->d_rowcount, e->d_envbuf, e->d_counters,
                                                                (e->cfg.flags & SKB_CFG_FORCE_GENERIC) ? 1 : 0);
     e->stats.kernel_launches++;
   }

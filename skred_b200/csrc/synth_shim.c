@@ -701,6 +701,35 @@ int skb_shim_snapshot_range(int first, int n) {
 
 void skb_shim_snapshot(void) { skb_shim_snapshot_range(0, VOICE_MAX); }
 
+/* The inverse: host arrays -> device (checkpoint resume; a harness that wrote voice_phase[]
+ * / voice_finished[] directly, the way wire.c writes other arrays). */
+int skb_shim_restore_range(int first, int n) {
+  if (first < 0 || n <= 0 || first + n > VOICE_MAX) return SKB_ERR_ARG;
+  engine();
+  skb_shim_flush();                       /* pending ops first: the arrays already include their effect */
+  skb_voice_state *st = (skb_voice_state *)calloc((size_t)n, sizeof(*st));
+  for (int k = 0; k < n; k++) {
+    const int v = first + k;
+    st[k].phase = voice_phase[v];
+    st[k].finished = voice_finished[v];
+    st[k].sample = voice_sample[v];
+    st[k].sh_hold = voice_sample_hold[v];
+    st[k].sh_count = voice_sample_hold_count[v];
+    st[k].x1 = voice_filter[v].x1; st[k].x2 = voice_filter[v].x2;
+    st[k].y1 = voice_filter[v].y1; st[k].y2 = voice_filter[v].y2;
+    st[k].env_active = voice_amp_envelope[v].is_active;
+    st[k].env_velocity = voice_amp_envelope[v].velocity;
+    st[k].env_start = voice_amp_envelope[v].sample_start;
+    st[k].env_release = voice_amp_envelope[v].sample_release;
+    st[k].smoother_gain = voice_smoother_gain[v];
+    st[k].pan_left = voice_pan_left[v];
+    st[k].pan_right = voice_pan_right[v];
+  }
+  int r = skb_restore(g_engine, first, n, st);
+  free(st);
+  return r;
+}
+
 static int64_t ts_ns(const struct timespec *a, const struct timespec *b) {
   return ((int64_t)b->tv_sec - a->tv_sec) * 1000000000LL + ((int64_t)b->tv_nsec - a->tv_nsec);
 }

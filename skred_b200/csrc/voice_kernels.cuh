@@ -25,8 +25,6 @@
 
 #define SKB_NPQ 8          /* float4 groups per voice: parameters (32 words) */
 #define SKB_NSQ 5          /* float4 groups per voice: evolving state (18 of 20 words) */
-#define SKB_FREE_THREADS 64
-#define SKB_CHUNK 32       /* frames per warp-level transpose-reduce */
 #define SKB_REF_NONE (-1)      /* no modulator: the reference's literal for that site (1.0f / no FM) */
 #define SKB_REF_SELF (-2)      /* the voice reads its own voice_sample */
 #define SKB_REF_ZERO (-3)      /* modulator contributes an identical 0.0f (depth-0 CZ default, out-of-range osc) */
@@ -302,346 +300,8 @@ __device__ __forceinline__ float2 voice_frame(const VoiceP &p, const VoiceK &k, 
   return make_float2(out * s.panL, out * s.panR);                                 /* :603-604 */
 }
 
-/* ======================================================================== */
-/* K1  render_free: voices with no live cross-voice reads                    */
-/* ======================================================================== */
-/* 1 thread = 1 voice (slot), looping the frames with every evolving word in
- * registers.  Stereo contributions go through a per-warp shared-memory tile
- * [SKB_CHUNK frames][32 lanes] that is read back TRANSPOSED: lane f adds the 32
- * voices of frame f in lane order (fixed order => run-to-run deterministic) and
- * stores one coalesced 256-byte row segment of `partials[warp_row][frame]`.
- *
- * Two code paths produce IDENTICAL bits (tests/test_gpu_parity.py checks it):
- *   generic   voice_frame<> per frame: every feature, every corner.
- *   fast      render_fast(): for warps in which no lane needs S&H / quantize /
- *             noise / reverse / self-modulation / mute / smoother-off.  With
- *             thread-per-voice a B200 holds only ~2-3.5 live warps per scheduler
- *             at 65,536 voices, so latency is hidden by ILP INSIDE the warp, not by
- *             occupancy: every 8-frame sub-chunk runs as a sequence of branch-free
- *             straight-line STAGES over register arrays —
- *               A1 phase recurrence (add, single-wrap select)       synth.c:226-258
- *               A2 table index (one switch on the CZ mode OUTSIDE the frame loop;
- *                  CZ slopes hoisted: d is constant without a modulator)  :149-215, 262-272
- *               A3 gather: 8 independent loads in flight            :274
- *               B  biquad recurrence                                :349-364
- *               C  envelope -> gain (constant while sustaining)     :398-431, 580-588
- *               D  smoother, scale, pan, tile store                 :589-606
- *             so the scheduler can overlap frames and the load latency leaves the
- *             per-frame dependency chain.  Hoisted values use the same operands and
- *             the same individually rounded ops as the reference, hence the same
- *             bits.  Anything uncommon in the phase step (one-shot end, multi-span
- *             wrap, underflow, non-finite phase) is detected in A1 and the whole
- *             sub-chunk is redone by the generic code from the saved phase. */
-#define SKB_TILE_STRIDE 33   /* float2 units; +1 keeps the transposed read conflict-free */
-#define SKB_SUB 8            /* frames per straight-line sub-chunk */
-
-/* per-voice CZ constants for a modulator-free voice (d is constant) */
-struct CzK { float d, k1, k2; };
-
-__device__ __forceinline__ void cz_consts(int mode, float d, CzK &c) {
-  d = (d < 0.0f) ? 0.0f : (d > 0.999f ? 0.999f : d);                              /* synth.c:154 */
-  c.d = d; c.k1 = 0.0f; c.k2 = 0.0f;
-  switch (mode) {
-    case 1: c.k1 = 0.5f / d; c.k2 = 0.5f / (1.0f - d); break;                     /* :157-166 */
-    case 2: case 3: c.k1 = 0.5f / (0.5f - d * 0.5f); break;                       /* :167-186 */
-    case 5: { const float hd = d * 0.5f; c.k1 = 0.5f / (0.5f - hd); c.k2 = 0.5f / (0.5f + hd); break; }
-    case 6: c.k1 = 1.0f + 4.0f * d; break;
-    case 7: c.k1 = 1.0f + 8.0f * d; break;
-    default: break;
-  }
-}
-
-/* envelope with the time base as int32 (valid while ssc - start < 2^31: the
- * u64 -> f32 and s32 -> f32 conversions round identically there) */
-struct EnvK { float AD, oneMinusS; int t0, tr0; bool released, use; };
-
-template <int MODE>
-__device__ __forceinline__ void cz_index8(const float (&ph)[SKB_SUB], int (&idx)[SKB_SUB], const CzK &c, const VoiceK &k) {
-#pragma unroll
-  for (int j = 0; j < SKB_SUB; j++) {
-    float x = (k.inv_size != 0.0f) ? ph[j] * k.inv_size : ph[j] / k.size_f;     /* :151 */
-    if (MODE == 1) x = (x < c.d) ? x * c.k1 : 0.5f + (x - c.d) * c.k2;
-    if (MODE == 2) x = (x < 0.5f) ? x * c.k1 : 1.0f - (1.0f - x) * c.k1;
-    if (MODE == 3) x = (x < 0.5f) ? x * c.k1 : 0.5f + (x - 0.5f) * c.k1;
-    if (MODE == 4) x = wrap_mod(x * 2.0f, 1.0f, 2.0f);                            /* fmodf(2x, 1) */
-    if (MODE == 5) x = (x < 0.5f) ? x * c.k1 : 0.5f + (x - 0.5f) * c.k2;
-    if (MODE == 6 || MODE == 7) x = dev_fast_pow(x, c.k1);
-    idx[j] = c_f2i(x * k.size_f);                                                 /* :214, :265 */
-  }
-}
-
-__device__ __forceinline__ void render_fast(const VoiceP &p, const VoiceK &k, VoiceS &s,
-                                            const float *__restrict__ tables, int nfull,
-                                            unsigned long long ssc_before, float2 *mytile,
-                                            float2 *__restrict__ out_row, int lane) {
-  CzK cz;
-  {
-    const float dm = (p.cz_ref == SKB_REF_NONE) ? 1.0f : 0.0f * p.cz_depth;       /* synth.c:264 */
-    cz_consts(p.cz_mode, p.cz_dist + dm, cz);
-  }
-  EnvK ek;
-  ek.use = (p.flags & SKB_F_USE_ENV) != 0;
-  ek.AD = p.envA + p.envD;
-  ek.oneMinusS = 1.0f - p.envS;
-  ek.t0 = (int)(unsigned)(ssc_before - s.env_start);
-  ek.tr0 = (int)(unsigned)(ssc_before - s.env_rel);
-  ek.released = s.env_rel != 0ull;
-  const float *tp = tables + (p.toff >= 0 ? p.toff : 0);
-  const int imax = p.tsize - 1;
-  const bool looping = !k.stop_at_end;
-  const bool silent = p.amp == 0.0f;
-  const NoMods nomods;
-  for (int base = 0; base < nfull; base += SKB_CHUNK) {
-#pragma unroll 1
-    for (int sb = 0; sb < SKB_CHUNK; sb += SKB_SUB) {
-      const int f0 = base + sb;
-      float L[SKB_SUB], R[SKB_SUB];
-#pragma unroll
-      for (int j = 0; j < SKB_SUB; j++) { L[j] = 0.0f; R[j] = 0.0f; }
-      const bool active = !s.finished && !silent;                                 /* :531-542 */
-      const float phase_in = s.phase;
-      float ph[SKB_SUB];
-      bool rare = false;
-      if (active) {
-        /* ---- A1: phase recurrence, :226-258 ---- */
-        float phase = phase_in;
-#pragma unroll
-        for (int j = 0; j < SKB_SUB; j++) {
-          float q = phase + p.inc;                                                /* :226 */
-          const bool in = (q >= k.lo) && (q < k.hi);
-          const float over = q - k.lo;
-          const bool simple = looping && (q >= k.hi) && (over < k.span2);         /* exactly one wrap */
-          q = simple ? k.lo + (over - k.span) : q;                                /* lo + fmodf(q - lo, span) */
-          rare = rare || !(in || simple);
-          phase = q;
-          ph[j] = q;
-        }
-        s.phase = phase;
-      } else {
-        s.sample = 0.0f;
-      }
-      if (__any_sync(0xffffffffu, rare)) {
-        /* uncommon phase event somewhere in the warp: redo these frames generically */
-        s.phase = phase_in;
-#pragma unroll 1
-        for (int j = 0; j < SKB_SUB; j++) {
-          const float2 o = voice_frame<false>(p, k, s, ssc_before + (unsigned long long)(f0 + j + 1), 0.0f, tables, nomods);
-          mytile[(sb + j) * SKB_TILE_STRIDE + lane] = o;
-        }
-        continue;
-      }
-      if (active) {
-        /* ---- A2: table index, :262-272 ---- */
-        int idx[SKB_SUB];
-        switch (p.cz_mode) {
-          case 0:
-#pragma unroll
-            for (int j = 0; j < SKB_SUB; j++) idx[j] = __float2int_rz(ph[j]);     /* :268 */
-            break;
-          case 1: cz_index8<1>(ph, idx, cz, k); break;
-          case 2: cz_index8<2>(ph, idx, cz, k); break;
-          case 3: cz_index8<3>(ph, idx, cz, k); break;
-          case 4: cz_index8<4>(ph, idx, cz, k); break;
-          case 5: cz_index8<5>(ph, idx, cz, k); break;
-          case 6: cz_index8<6>(ph, idx, cz, k); break;
-          case 7: cz_index8<7>(ph, idx, cz, k); break;
-          default:                                                                /* cz_phasor returns p, :210 */
-#pragma unroll
-            for (int j = 0; j < SKB_SUB; j++) idx[j] = c_f2i(ph[j]);
-            break;
-        }
-        /* ---- A3: gather, :271-274 ---- */
-        float x[SKB_SUB];
-#pragma unroll
-        for (int j = 0; j < SKB_SUB; j++) x[j] = __ldg(tp + max(min(idx[j], imax), 0));
-        /* ---- B: biquad, :349-364 ---- */
-        if (p.fmode) {
-          float x1 = s.x1, x2 = s.x2, y1 = s.y1, y2 = s.y2;
-#pragma unroll
-          for (int j = 0; j < SKB_SUB; j++) {
-            const float y = p.b0 * x[j] + p.b1 * x1 + p.b2 * x2 - p.a1 * y1 - p.a2 * y2;
-            x2 = x1; x1 = x[j]; y2 = y1; y1 = y;
-            x[j] = y;
-          }
-          s.x1 = x1; s.x2 = x2; s.y1 = y1; s.y2 = y2;
-        }
-        /* ---- C: gain = amp * env * 1, :580-588 ---- */
-        float gain[SKB_SUB];
-        {
-          float gconst = p.amp;
-          bool per_frame = false;
-          if (ek.use) {
-            if (!s.env_active) {
-              gconst = p.amp * (0.0f * s.env_vel);                                /* step returns 0, :399 */
-            } else {
-              const float tf = __int2float_rn(ek.t0 + f0 + 1);
-              if (!(tf < p.envA) && !(tf < ek.AD) && !ek.released) gconst = p.amp * (p.envS * s.env_vel);  /* sustain, :413-415 */
-              else per_frame = true;
-            }
-          }
-          if (!per_frame) {
-#pragma unroll
-            for (int j = 0; j < SKB_SUB; j++) gain[j] = gconst;
-          } else {
-#pragma unroll
-            for (int j = 0; j < SKB_SUB; j++) {                                   /* attack / decay / release, :398-431 */
-              float e = 0.0f;
-              if (s.env_active) {
-                const float t = __int2float_rn(ek.t0 + f0 + j + 1);
-                if (t < p.envA) e = t / p.envA;
-                else if (t < ek.AD) e = 1.0f - ((t - p.envA) / p.envD) * ek.oneMinusS;
-                else if (!ek.released) e = p.envS;
-                else {
-                  const float tr = __int2float_rn(ek.tr0 + f0 + j + 1);
-                  if (tr < p.envR) e = p.envS * (1.0f - tr / p.envR);
-                  else s.env_active = 0;
-                }
-              }
-              gain[j] = p.amp * (e * s.env_vel);
-            }
-          }
-        }
-        /* ---- D: smoother, scale, pan, :589-604 ---- */
-        float g = s.sm_gain, last = 0.0f;
-#pragma unroll
-        for (int j = 0; j < SKB_SUB; j++) {
-          g = g + p.sm_k * (gain[j] - g);
-          last = x[j] * g;
-          L[j] = last * s.panL;
-          R[j] = last * s.panR;
-        }
-        s.sm_gain = g;
-        s.sample = last;
-        s.nact += SKB_SUB;
-      }
-#pragma unroll
-      for (int j = 0; j < SKB_SUB; j++) mytile[(sb + j) * SKB_TILE_STRIDE + lane] = make_float2(L[j], R[j]);
-    }
-    __syncwarp();
-    {
-      float Ls = 0.0f, Rs = 0.0f;
-#pragma unroll
-      for (int v = 0; v < 32; v++) {
-        const float2 c = mytile[lane * SKB_TILE_STRIDE + v];
-        Ls += c.x; Rs += c.y;
-      }
-      out_row[base + lane] = make_float2(Ls, Rs);
-    }
-    __syncwarp();
-  }
-}
-
-/* does this lane force the warp onto the generic path? */
-__device__ __forceinline__ bool lane_needs_generic(const VoiceP &p, const VoiceS &s, int nframes,
-                                                   unsigned long long ssc_before) {
-  if (s.finished || p.amp == 0.0f) return false;     /* skipped for the whole launch either way */
-  if ((p.flags & (SKB_F_NOISE | SKB_F_REVERSE | SKB_F_DISCONNECT)) || !(p.flags & SKB_F_SMOOTHER) ||
-      p.sh_max != 0 || p.quant != 0 || p.am_ref != SKB_REF_NONE || p.pm_ref != SKB_REF_NONE ||
-      (p.cz_mode != 0 && p.cz_ref != SKB_REF_NONE && p.cz_ref != SKB_REF_ZERO) || p.toff < 0 || p.tsize <= 0)
-    return true;
-  if (p.flags & SKB_F_USE_ENV) {
-    const unsigned long long lim = 0x7fffffffull - (unsigned long long)nframes - 1ull;
-    if (ssc_before < s.env_start || ssc_before - s.env_start > lim) return true;
-    if (s.env_rel != 0ull && (ssc_before < s.env_rel || ssc_before - s.env_rel > lim)) return true;
-  }
-  return false;
-}
-
-/* Persistent form: ONE CTA per SM (grid = min(#SM, rows)), SKB_CTA_WARPS warps.  The free
- * range is cut into ROWS of 32 consecutive slots (slots are sorted by feature key, so a row
- * is homogeneous); row r belongs to CTA r % gridDim.x, which deals every feature class
- * evenly over the SMs.  A CTA takes its rows in BATCHES of SKB_CTA_WARPS and first
- * COMPACTS the batch: voices that are skipped for the whole launch (finished one-shots,
- * amp == 0; synth.c:531-542 — state edits only happen at launch boundaries) are dropped
- * and the live ones are packed, in slot order, into as few warps as possible.  Each live
- * warp writes one partial row; rowcount[group] tells k_reduce_rows how many. */
-#define SKB_CTA_WARPS 16
-#define SKB_CTA_THREADS (SKB_CTA_WARPS * 32)
-#define SKB_TILE_FLOAT2 (SKB_CHUNK * SKB_TILE_STRIDE)
-
-__global__ void __launch_bounds__(SKB_CTA_THREADS, 1)
-k_render_free(const float4 *__restrict__ pq, float4 *__restrict__ sq, int cap, int n_rows, int n_free,
-              const float *__restrict__ tables, const float *__restrict__ noise,
-              int nframes, unsigned long long ssc_before,
-              float2 *__restrict__ partials, int row_stride, int *__restrict__ rowcount,
-              unsigned long long *__restrict__ counters, int force_generic) {
-  extern __shared__ float2 tile_all[];           /* [SKB_CTA_WARPS][SKB_CHUNK * SKB_TILE_STRIDE] */
-  __shared__ int s_cnt[SKB_CTA_WARPS];
-  __shared__ int s_list[SKB_CTA_THREADS];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ncta = gridDim.x, cta = blockIdx.x;
-  const int rows_mine = (n_rows - cta + ncta - 1) / ncta;
-  float2 *mytile = tile_all + warp * SKB_TILE_FLOAT2;
-  for (int k0 = 0; k0 < rows_mine; k0 += SKB_CTA_WARPS) {
-    /* ---- compaction of this batch ---- */
-    const int k = k0 + warp;
-    const int cand = (cta + ncta * k) * 32 + lane;
-    bool alive = false;
-    if (k < rows_mine && cand < n_free) {
-      float4 s0 = sq[cand];                                        /* phase, finished, sample, sh_hold */
-      const float amp = pq[cand].x;
-      alive = (__float_as_int(s0.y) == 0) && (amp != 0.0f);
-      if (!alive && s0.z != 0.0f) { s0.z = 0.0f; sq[cand] = s0; }  /* skipped voice: voice_sample = 0 */
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, alive);
-    if (lane == 0) s_cnt[warp] = __popc(bal);
-    __syncthreads();
-    int before = 0, total = 0;
-#pragma unroll
-    for (int i = 0; i < SKB_CTA_WARPS; i++) { const int c = s_cnt[i]; if (i < warp) before += c; total += c; }
-    if (alive) s_list[before + __popc(bal & ((1u << lane) - 1u))] = cand;
-    __syncthreads();
-    const int group = (k0 / SKB_CTA_WARPS) * ncta + cta;
-    const int live_warps = (total + 31) >> 5;
-    if (threadIdx.x == 0) rowcount[group] = live_warps;
-    if (warp < live_warps) {
-      const bool live = (int)threadIdx.x < total;
-      const int slot = live ? s_list[threadIdx.x] : 0;
-      VoiceP p; VoiceS s; VoiceK kk;
-      load_params(pq, cap, slot, p);
-      load_state(sq, cap, slot, s);
-      if (!live) { p.amp = 0.0f; p.flags = SKB_F_SMOOTHER; p.sh_max = 0; p.quant = 0; p.cz_mode = 0;
-                   p.am_ref = SKB_REF_NONE; p.pm_ref = SKB_REF_NONE; p.toff = 0; p.tsize = 1; }   /* padding lane: silent */
-      derive_consts(p, kk);
-      float2 *out_row = partials + (size_t)(group * SKB_CTA_WARPS + warp) * row_stride;
-      const bool generic = force_generic || __any_sync(0xffffffffu, lane_needs_generic(p, s, nframes, ssc_before));
-      int done = 0;
-      if (!generic) {
-        done = nframes & ~(SKB_CHUNK - 1);
-        render_fast(p, kk, s, tables, done, ssc_before, mytile, out_row, lane);
-      }
-      /* generic path: everything for a warp with uncommon features, the ragged tail otherwise */
-      const bool wants_noise = (p.flags & SKB_F_NOISE) != 0;
-      const NoMods nomods;
-      for (int base = done; base < nframes; base += SKB_CHUNK) {
-        const int cnt = min(SKB_CHUNK, nframes - base);
-        for (int f = 0; f < cnt; f++) {
-          const float white = wants_noise ? __ldg(noise + base + f) : 0.0f;
-          const float2 o = voice_frame<false>(p, kk, s, ssc_before + (unsigned long long)(base + f + 1), white, tables, nomods);
-          mytile[f * SKB_TILE_STRIDE + lane] = o;
-        }
-        __syncwarp();
-        if (lane < cnt) {
-          float L = 0.0f, R = 0.0f;
-#pragma unroll
-          for (int v = 0; v < 32; v++) {
-            const float2 c = mytile[lane * SKB_TILE_STRIDE + v];
-            L += c.x; R += c.y;
-          }
-          out_row[base + lane] = make_float2(L, R);
-        }
-        __syncwarp();
-      }
-      if (live) store_state(sq, cap, slot, s);
-      /* rendered (not skipped) voice-frames of this launch: the metric's numerator */
-      int na = live ? s.nact : 0;
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) na += __shfl_xor_sync(0xffffffffu, na, d);
-      if (lane == 0 && na) atomicAdd(counters, (unsigned long long)na);
-    }
-    __syncthreads();          /* s_cnt / s_list are reused by the next batch */
-  }
-}
+/* K1  render_free: free_kernel.cuh */
+#include "free_kernel.cuh"
 
 /* ======================================================================== */
 /* K2  render_bins: modulation groups, frame-lock-step                       */

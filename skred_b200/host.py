@@ -133,6 +133,21 @@ class SynthAPI:
         if self._mark:
             self._mark(v)
 
+    # ---- evolving state written directly (checkpoint resume / stationary workloads) ----
+    def set_phase(self, v, phase, finished):
+        self.array("voice_phase")[v] = phase
+        self.array("voice_finished", C.c_int)[v] = finished
+        self._state_dirty = True
+
+    def commit_state(self):
+        """On the reference the arrays ARE the state; the drop-in pushes them to the device."""
+        if getattr(self, "_state_dirty", False) and hasattr(self.lib, "skb_shim_engine"):
+            self.lib.skb_shim_restore_range.argtypes = [C.c_int, C.c_int]
+            r = self.lib.skb_shim_restore_range(0, self.voice_max)
+            if r != 0:
+                raise RuntimeError("skb_shim_restore_range failed: %d" % r)
+        self._state_dirty = False
+
     def call(self, name, *args):
         if name in SETTERS:
             return getattr(self.lib, name)(*args)

@@ -153,9 +153,15 @@ def config4(V=4096, seconds=30.0, rate_hz=8.0, seed=0x5EED0002):
             "timed": timed, "events": bucket(timed), "frames": int(seconds * SR)}
 
 
-def config5(V=65536, seconds=600.0, luts=None, event_seconds=None, seed=0x5EED0005):
+def config5(V=65536, seconds=600.0, luts=None, event_seconds=None, seed=0x5EED0005, stationary=False):
     """Mixed load: v%3 -> config-2 / config-3 / config-4 recipe, amplitudes 40/V,
-    one (re)trigger per voice per 10 s."""
+    one (re)trigger per voice per 10 s.
+
+    stationary=True starts the one-shot PCM third in its long-run state instead of all
+    triggered at t = 0: voice v was last triggered tau_v ~ U(0, 10 s) ago, so it is either
+    somewhere inside its sample (phase = tau * inc, written to voice_phase[] by `install`) or
+    already finished, and its next trigger comes at 10 s - tau_v.  A short benchmark window
+    then sees the same mix of rendering and skipped voices as minute 5 of the 10 min job."""
     tables = {}
     if luts is not None:
         tables = {200: (luts["sine_lutable_0"], {}), 201: (luts["triangle_lutable_0"], {}),
@@ -175,19 +181,39 @@ def config5(V=65536, seconds=600.0, luts=None, event_seconds=None, seed=0x5EED00
     timed = []
     horizon = seconds if event_seconds is None else min(seconds, event_seconds)
     rng = XorShift64(seed)
+    pcm_tau = {}
     for v in range(V):
         t = 10.0 * rng.uniform()
+        if v % 3 == 2 and stationary:
+            pcm_tau[v] = int(t * SR)               # frames since the last trigger
+            t = 10.0 - t
         while t < horizon:
             if v % 3 == 2:
                 timed.append((int(t * SR), ("voice_trigger", v)))
             else:
                 timed.append((int(t * SR), ("envelope_velocity", v, 1.0)))
             t += 10.0
-        if v % 3 == 2:
+        if v % 3 == 2 and not stationary:
             setup.append(("voice_trigger", v))     # one-shots are silent until triggered
     timed.sort(key=lambda x: x[0])
     return {"name": "config5_mixed_%d" % V, "voices": V, "tables": tables, "setup": setup,
-            "timed": timed, "events": bucket(timed), "frames": int(seconds * SR)}
+            "timed": timed, "events": bucket(timed), "frames": int(seconds * SR), "pcm_tau": pcm_tau}
+
+
+def shard(wl, v0, n):
+    """The sub-workload of voices [v0, v0 + n), re-indexed from 0 (an independent instance of
+    the reference with VOICE_MAX = n renders it; valid when no modulation edge leaves the range)."""
+    def mv(c):
+        return (c[0], c[1] - v0) + tuple(c[2:])
+    inside = lambda c: v0 <= c[1] < v0 + n      # noqa: E731
+    out = dict(wl)
+    out["voices"] = n
+    out["setup"] = [mv(c) for c in wl["setup"] if inside(c)]
+    out["timed"] = [(t, mv(c)) for t, c in wl.get("timed", []) if inside(c)]
+    out["events"] = {k: [mv(c) for c in calls if inside(c)] for k, calls in wl["events"].items()}
+    out["events"] = {k: c for k, c in out["events"].items() if c}
+    out["pcm_tau"] = {v - v0: t for v, t in wl.get("pcm_tau", {}).items() if v0 <= v < v0 + n}
+    return out
 
 
 def install(api, wl):
@@ -196,3 +222,14 @@ def install(api, wl):
     for slot, (data, kw) in wl["tables"].items():
         install_table(api, slot, data, **kw)
     api.apply(wl["setup"])
+    if wl.get("pcm_tau"):
+        import ctypes as C
+        import numpy as np
+        inc = api.array("voice_phase_inc")
+        size = api.array("voice_table_size", C.c_int)
+        for v, tau in wl["pcm_tau"].items():
+            ph = np.float32(tau) * np.float32(inc[v])
+            if ph < np.float32(size[v] - 1):
+                api.set_phase(v, float(ph), 0)     # mid-sample
+            # else: finished (wave_set of a one-shot leaves it finished, synth.c:281-282)
+        api.commit_state()

@@ -113,3 +113,49 @@ def test_specialised_path_equals_generic_path(name, luts, monkeypatch):
     ob = cases.drive_render(b, wl)
     assert np.array_equal(oa.view(np.uint32), ob.view(np.uint32))
     assert_state_equal(a.state(), b.state())
+
+
+def test_rendered_voice_frame_count_matches_port(luts):
+    """skb_stats.active_voice_frames (the numerator of voice-samples/s: voices the loop does not
+    skip, synth.c:531-542) is the same integer on the GPU as in the CPU restatement."""
+    for name in ("pcm_retrigger", "misc", "lut_adsr", "mods"):
+        wl = cases.SYNTHETIC[name](luts)
+        a, b = O.PortSkred(wl["voices"]), O.DropinCuda(wl["voices"])
+        for s in (a, b):
+            cases.drive_setup(s, wl)
+            cases.drive_render(s, wl)
+        na, nb = a.engine_stats().active_voice_frames, b.engine_stats().active_voice_frames
+        assert na == nb and na > 0, (name, na, nb)
+
+
+def test_config5_stationary_1024_vs_reference(luts):
+    """The bench workload at V = 1,024 (mixed LUT / Korg+CZ+biquad / one-shot PCM started mid-sample
+    through voice_phase[] + skb_shim_restore_range), 1 s with its retrigger events, against the
+    compiled reference: every evolving word bit-exact, mix within 1e-5."""
+    from skred_b200 import workloads as W
+    V, frames = 1024, 86 * 512
+    wl = W.config5(V, seconds=600.0, luts=luts, event_seconds=frames / 44100.0 + 1.0, stationary=True)
+    ref = O.RefSkred(V) if O.have_ref(V) else O.PortSkred(V)
+    gpu = O.DropinCuda(V)
+    outs = []
+    for s in (ref, gpu):
+        W.install(s, wl)
+        outs.append(s.render(frames, events=wl["events"]))
+    assert maxdiff(outs[0], outs[1]) <= FULL_SCALE_TOL
+    assert_state_equal(ref.state(), gpu.state(), exact_keys=EXACT)
+    fin = gpu.state()["finished"]
+    assert 0 < int(fin.sum()) < V          # some one-shots are over, some still play
+
+
+def test_long_launch_equals_callbacks_with_envelopes_and_one_shots(luts):
+    """One synth() call of 8,192 frames (16 envelope windows inside one launch, one-shots ending
+    inside it) equals 16 callbacks of 512, bit for bit."""
+    from skred_b200 import workloads as W
+    wl = W.config5(1024, seconds=600.0, luts=luts, event_seconds=0.0, stationary=True)
+    a, b = O.DropinCuda(1024, run_seq=False), O.DropinCuda(1024, run_seq=False)
+    for s in (a, b):
+        W.install(s, wl)
+    oa = a.render(8192 + 300, block=512)
+    ob = b.render(8192 + 300, block=8192 + 300)
+    assert np.array_equal(oa.view(np.uint32), ob.view(np.uint32))
+    assert_state_equal(a.state(), b.state())

@@ -66,3 +66,28 @@ def test_port_matches_reference_synthetic_state(name, luts):
     oa, ob = cases.drive_render(a, wl), cases.drive_render(b, wl)
     assert np.array_equal(oa.view(np.uint32), ob.view(np.uint32))
     assert_state_equal(a.state(), b.state())
+
+
+@pytest.mark.skipif(not O.have_ref(1024), reason="compiled reference (oracle/_ref, V=1024) not present")
+def test_port_matches_reference_bench_workload_1024(luts):
+    """The bench workload (config 5, one-shots started mid-sample through voice_phase[] and
+    skb_shim_restore_range) at V = 1,024: shim + port == reference bit for bit, and the
+    rendered-voice-frame counter counts exactly the voices the reference loop does not skip."""
+    from skred_b200 import workloads as W
+    V, frames = 1024, 12 * 512
+    wl = W.config5(V, seconds=600.0, luts=luts, event_seconds=frames / 44100.0 + 1.0, stationary=True)
+    a, b = O.RefSkred(V), O.PortSkred(V)
+    for s in (a, b):
+        W.install(s, wl)
+    oa = np.zeros((frames, 2), np.float32)
+    ob = np.zeros((frames, 2), np.float32)
+    for k in range(frames // 512):
+        for s, o in ((a, oa), (b, ob)):
+            if k in wl["events"]:
+                s.apply(wl["events"][k])
+            s._synth(o[k * 512:(k + 1) * 512], 512)
+    assert np.array_equal(oa.view(np.uint32), ob.view(np.uint32))
+    assert_state_equal(a.state(), b.state())
+    n = b.engine_stats().active_voice_frames
+    # two thirds of the voices always render, the one-shot third only while a sample plays
+    assert 2 * V // 3 * frames <= n < V * frames
