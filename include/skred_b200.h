@@ -197,6 +197,10 @@ int  skb_render_mix(skb_engine *e, int nframes, uint64_t ssc_before,
                     const float *noise, float *d_mix, void *stream);
 int  skb_finish(skb_engine *e, const float *d_mix, int nframes, const float *gain,
                 float *out, int num_channels, void *stream);
+/* The engine's own raw-mix buffer (DEVICE memory, max_frames x 2 floats) for callers of the
+ * split form that do not bring one: synth() renders the event-free segments of one call into
+ * it back to back and finishes once (one synchronisation per call, not per segment). */
+float *skb_mix_buffer(skb_engine *e);
 /* Wait for everything queued on `stream` (NULL = engine stream). */
 int  skb_sync(skb_engine *e, void *stream);
 
@@ -224,8 +228,19 @@ typedef struct skb_stats {
   int32_t  _pad;
   uint64_t active_voice_frames; /* voice-frames actually rendered (not skipped by synth.c:531-542) as of the
                                    last skb_finish / skb_sync: the numerator of voice-samples/s */
+  uint64_t class_rows[8];     /* diagnostics: live 32-voice rows seen by k_render_free per code-path class
+                                 (0..5 = CZ none/piecewise/pow x filter off/on, 6 = mixed row, 7 = generic) */
+  uint64_t phase_cycles[8];   /* diagnostics: SM clocks thread 0 of every CTA spent per phase of k_render_free
+                                 (compaction, voice set-up, table cache, envelope pre-pass, render, wait for the
+                                 slowest warp, row sum, final store), summed over CTAs and launches */
+  uint64_t cta_batches;       /* ... and how many (CTA, batch) passes that covers */
 } skb_stats;
 int  skb_get_stats(skb_engine *e, skb_stats *out);
+
+/* Diagnostics for tuning (tools/bench_probe.py): per-CTA phase clocks of the last launch of the
+ * free-voice kernel and the planner's row lists; class rank of the voice in a slot. */
+int  skb_debug_cta_phases(skb_engine *e, uint64_t *phases, int32_t *rows, int max_ctas, int *rows_cap);
+int  skb_debug_slot_rank(skb_engine *e, int slot);
 
 /* "cuda-sm100a" for the product, "cpu-port" for the oracle build. */
 const char *skb_backend_name(void);

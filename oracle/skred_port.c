@@ -406,6 +406,15 @@ int skb_render(skb_engine *e, int nframes, uint64_t ssc, const float *gain, cons
 
 int skb_sync(skb_engine *e, void *stream) { (void)stream; return e ? e->err : SKB_ERR_ARG; }
 
+float *skb_mix_buffer(skb_engine *e) { return e ? e->mix : NULL; }
+
+/* no kernels, no phases */
+int skb_debug_cta_phases(skb_engine *e, uint64_t *phases, int32_t *rows, int max_ctas, int *rows_cap) {
+  (void)e; (void)phases; (void)rows; (void)max_ctas; (void)rows_cap;
+  return 0;
+}
+int skb_debug_slot_rank(skb_engine *e, int slot) { (void)e; (void)slot; return -1; }
+
 int skb_snapshot(skb_engine *e, int first, int n, skb_voice_state *out) {
   if (!e || first < 0 || n < 0 || first + n > e->n || !out) return fail(e, SKB_ERR_ARG, "snapshot: bad range");
   flush_ops(e);

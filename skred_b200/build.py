@@ -61,7 +61,7 @@ def shim_so(v):
 
 
 def build_engine(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "voice_kernels.cuh", "partition.h")] + [
+    srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "voice_kernels.cuh", "free_kernel.cuh", "partition.h")] + [
         os.path.join(INC, "skred_b200.h"), __file__]
     if not force and newer(ENGINE_SO, srcs):
         return ENGINE_SO
@@ -72,6 +72,16 @@ def build_engine(force=False, verbose=False):
     if verbose:
         print(out)
     return ENGINE_SO
+
+
+def build_engine_variant(name, defines):
+    """A tuning build of the engine (same soname) under skred_b200/variants/<name>/:
+    select it with SKB_ENGINE_LIB=<path>.  defines: e.g. ["-DSKB_SUB=4", "-DSKB_CTA_WARPS=12"]."""
+    d = os.path.join(HERE, "variants", name)
+    os.makedirs(d, exist_ok=True)
+    out = os.path.join(d, "libskred_b200.so")
+    run([NVCC] + NVCC_FLAGS + list(defines) + ["-I" + INC, "-I" + CSRC, os.path.join(CSRC, "engine.cu"), "-o", out])
+    return out
 
 
 def have_skred_src():

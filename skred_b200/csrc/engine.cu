@@ -23,12 +23,14 @@
 #include <string.h>
 
 #include <algorithm>
+#include <queue>
 #include <vector>
 
 #include "skred_b200.h"
 #include "partition.h"
 #include "voice_kernels.cuh"
 
+#define SKB_N_COUNTERS 20      /* rendered voice-frames (free, bins), live rows per class, phase clocks, CTA batches */
 #define SKB_BIN_PACK 128      /* small components are packed into bins of <= this many voices */
 #define SKB_BIN_MAX 1024      /* one CTA per bin: hard upper bound of a component */
 
@@ -59,7 +61,11 @@ struct skb_engine {
   std::vector<skb_bin_desc> bins;
   std::vector<uint64_t> edge_sig;                   /* per voice: hash of its live edges (re-plan trigger) */
   int n_free = 0, n_free_pad = 0, n_slots = 0, n_free_rows = 0, max_bin_threads = 0;
-  int n_sm = 148, free_ctas = 0, free_groups = 0, n_groups = 0;   /* partial rows come in groups of SKB_CTA_WARPS */
+  int rows_cap = 0;                  /* entries per CTA in d_ctarows */
+  int *d_ctarows = nullptr; size_t ctarows_cap = 0;
+  std::vector<int> h_ctarows;
+  unsigned long long *d_ctaphase = nullptr; size_t ctaphase_cap = 0;   /* diagnostics: per-CTA phase clocks of the last launch */
+  int n_sm = 148, free_ctas = 0, free_groups = 0, n_prows = 0;   /* partial rows: one per (CTA, batch) of k_render_free, one per bin */
 
   /* device */
   float4 *d_pq = nullptr, *d_sq[2] = {nullptr, nullptr};
@@ -69,7 +75,6 @@ struct skb_engine {
   std::vector<TableDesc> tables;
   skb_bin_desc *d_bins = nullptr; int d_bins_cap = 0;
   float2 *d_partials = nullptr; size_t partials_cap = 0;
-  int *d_rowcount = nullptr; size_t rowcount_cap = 0;
   float *d_envbuf = nullptr; size_t envbuf_cap = 0;   /* envelope pre-pass rows: [CTA][thread][SKB_ENV_WIN] */
   float2 *d_part2 = nullptr;
   unsigned int *d_tickets = nullptr;
@@ -155,7 +160,7 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
   e->n_sm = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
   memset(&e->stats, 0, sizeof(e->stats));
   const int n = e->n, mf = e->cfg.max_frames;
-  e->cap = ((n + 31) / 32) * 32 + 64;
+  e->cap = ((n + 31) / 32) * 32 + 64 + 32 * 8;        /* + class padding of the free range */
   e->par.resize(n);
   for (int v = 0; v < n; v++) {
     memset(&e->par[v], 0, sizeof(skb_voice_params));
@@ -179,10 +184,10 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
             cudaMalloc((void **)&e->d_noise, (size_t)mf * sizeof(float)) == cudaSuccess &&
             cudaMalloc((void **)&e->d_part2, (size_t)SKB_RED_CHUNKS * mf * sizeof(float2)) == cudaSuccess &&
             cudaMalloc((void **)&e->d_tickets, (size_t)(mf / SKB_RED_X + 1) * sizeof(unsigned int)) == cudaSuccess &&
-            cudaMalloc((void **)&e->d_counters, 2 * sizeof(unsigned long long)) == cudaSuccess &&
-            cudaMallocHost((void **)&e->h_counters, 2 * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMalloc((void **)&e->d_counters, SKB_N_COUNTERS * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMallocHost((void **)&e->h_counters, SKB_N_COUNTERS * sizeof(unsigned long long)) == cudaSuccess &&
             cudaMemset(e->d_tickets, 0, (size_t)(mf / SKB_RED_X + 1) * sizeof(unsigned int)) == cudaSuccess &&
-            cudaMemset(e->d_counters, 0, 2 * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMemset(e->d_counters, 0, SKB_N_COUNTERS * sizeof(unsigned long long)) == cudaSuccess &&
             cudaFuncSetAttribute(k_render_free, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)skb_free_smem_bytes()) == cudaSuccess &&
             cudaMallocHost((void **)&e->h_gain, (size_t)mf * sizeof(float)) == cudaSuccess &&
@@ -213,8 +218,8 @@ void skb_destroy(skb_engine *e) {
   cudaFree(e->d_bins); cudaFree(e->d_partials); cudaFree(e->d_mix); cudaFree(e->d_out);
   cudaFree(e->d_gain); cudaFree(e->d_noise); cudaFree(e->d_idx); cudaFree(e->d_recs);
   cudaFree(e->d_ops); cudaFree(e->d_runs); cudaFree(e->d_snap);
-  cudaFree(e->d_envbuf);
-  cudaFree(e->d_rowcount); cudaFree(e->d_part2); cudaFree(e->d_tickets); cudaFree(e->d_counters);
+  cudaFree(e->d_envbuf); cudaFree(e->d_ctarows); cudaFree(e->d_ctaphase);
+  cudaFree(e->d_part2); cudaFree(e->d_tickets); cudaFree(e->d_counters);
   cudaFreeHost(e->h_counters);
   cudaFreeHost(e->h_gain); cudaFreeHost(e->h_noise); cudaFreeHost(e->h_out); cudaFreeHost(e->h_idx);
   cudaFreeHost(e->h_recs); cudaFreeHost(e->h_ops); cudaFreeHost(e->h_runs); cudaFreeHost(e->h_snap);
@@ -232,8 +237,8 @@ int skb_table_upload(skb_engine *e, const float *data, int size) {
   if (!e || !data || size <= 0) return fail(e, SKB_ERR_ARG, "table_upload: bad argument");
   cudaSetDevice(e->cfg.device);
   const size_t need = e->tables_used + (size_t)((size + 31) & ~31);   /* 128-byte aligned starts */
-  if (need > e->tables_cap) {
-    size_t ncap = std::max(need, e->tables_cap * 2);
+  if (need + SKB_TBL_CHUNK > e->tables_cap) {               /* slack: the table cache copies whole chunks */
+    size_t ncap = std::max(need + SKB_TBL_CHUNK, e->tables_cap * 2);
     float *nt = nullptr;
     CK(cudaMalloc((void **)&nt, ncap * sizeof(float)));
     CK(cudaStreamSynchronize(e->last_stream ? e->last_stream : e->stream));
@@ -277,20 +282,29 @@ static uint64_t edge_signature(const skb_voice_params *p, int v, int n) {
 }
 
 /* Sort key of a free voice: voices that take the same branches share warps. */
+/* Sort key of a free voice.  Primary: which body of k_render_free it needs, in ascending
+ * order of cost — rows of one class are packed together by the kernel, and later (costlier)
+ * rows get the higher warp ids, which the SM's issue arbiter prefers: the long warps run
+ * at full speed from the start and the short ones fill the gaps.  Then: same branches,
+ * same wave table (neighbouring rows go to the same CTA and share its table cache). */
+#define SKB_KEY_CLASS_SHIFT 40
 static uint64_t feature_key(const skb_voice_params *p) {
   uint64_t k = 0;
   const bool silent = (p->amp == 0.0f);
-  /* voices that need the generic per-frame code keep to their own warps */
   const bool generic = (p->flags & (SKB_F_NOISE | SKB_F_REVERSE | SKB_F_DISCONNECT)) || !(p->flags & SKB_F_SMOOTHER) ||
                        p->sample_hold_max != 0 || p->quantize != 0 || p->amp_mod_osc >= 0 || p->pan_mod_osc >= 0 ||
-                       ((p->flags & SKB_F_LOOP_ENABLED) && (p->flags & SKB_F_LOOP_VALID));
-  k |= (uint64_t)(generic ? 1 : 0) << 42;
-  k |= (uint64_t)(silent ? 1 : 0) << 41;
-  k |= (uint64_t)((p->flags & SKB_F_ONE_SHOT) ? 1 : 0) << 40;
-  k |= (uint64_t)((p->flags & SKB_F_NOISE) ? 1 : 0) << 39;
-  k |= (uint64_t)(p->cz_mode & 7) << 36;
-  k |= (uint64_t)(p->filter_mode ? 1 : 0) << 35;
-  k |= (uint64_t)((p->flags & SKB_F_USE_ENV) ? 1 : 0) << 34;
+                       ((p->flags & SKB_F_LOOP_ENABLED) && (p->flags & SKB_F_LOOP_VALID) && p->loop_start_f != 0.0f) ||
+                       p->cz_mode < 0 || p->cz_mode > 7;
+  const int czv = (p->cz_mode == 0) ? 0 : (p->cz_mode >= 6 ? 2 : 1);
+  static const int rank_of[6] = {0, 2, 1, 3, 4, 5};      /* (czv, filter): none, none+f, pw, pw+f, pow, pow+f */
+  int rank = rank_of[czv * 2 + (p->filter_mode ? 1 : 0)] + 1;
+  if (generic) rank = 7;
+  if (silent) rank = 0;                                  /* skipped by the loop: never rendered */
+  k |= (uint64_t)rank << SKB_KEY_CLASS_SHIFT;
+  k |= (uint64_t)((p->flags & SKB_F_ONE_SHOT) ? 1 : 0) << 39;
+  k |= (uint64_t)((p->flags & SKB_F_USE_ENV) ? 1 : 0) << 38;
+  k |= (uint64_t)(p->cz_mode & 7) << 35;
+  k |= (uint64_t)((p->flags & SKB_F_NOISE) ? 1 : 0) << 34;
   k |= (uint64_t)(p->quantize ? 1 : 0) << 33;
   k |= (uint64_t)(p->sample_hold_max ? 1 : 0) << 32;
   k |= (uint64_t)((uint32_t)(p->table_id + 1) & 0x7fffffffu);
@@ -318,7 +332,7 @@ static void pack_record(const skb_engine *e, int v, float4 *r) {
   /* CZ: negative osc -> the literal 1.0f (synth.c:264); depth 0 / out of range -> 0.0f */
   int cz_ref;
   if (p.cz_mod_osc < 0) cz_ref = SKB_REF_NONE;
-  else if (p.cz_mod_osc == v) cz_ref = SKB_REF_SELF;
+  else if (p.cz_mod_osc == v) cz_ref = (p.cz_mod_depth != 0.0f) ? SKB_REF_SELF : SKB_REF_ZERO;   /* sample * 0.0f (App. A-4) */
   else if (live[1] >= 0) cz_ref = make_ref(e, v, live[1], true);
   else cz_ref = SKB_REF_ZERO;
   const int am_ref = make_ref(e, v, p.amp_mod_osc, true);
@@ -374,10 +388,16 @@ static int replan(skb_engine *e, cudaStream_t st) {
   std::fill(e->level.begin(), e->level.end(), 0);
   e->voice_of_slot.assign(e->cap, -1);
   e->n_free = (int)fr.size();
-  e->n_free_pad = (e->n_free + 31) & ~31;
-  for (int i = 0; i < e->n_free; i++) {
-    e->slot_of_voice[fr[i].second] = i;
-    e->voice_of_slot[i] = fr[i].second;
+  {
+    /* a row of 32 slots never mixes classes: pad to the next row where the class changes */
+    int sl = 0;
+    for (int i = 0; i < e->n_free; i++) {
+      if (i > 0 && (fr[i].first >> SKB_KEY_CLASS_SHIFT) != (fr[i - 1].first >> SKB_KEY_CLASS_SHIFT)) sl = (sl + 31) & ~31;
+      e->slot_of_voice[fr[i].second] = sl;
+      e->voice_of_slot[sl] = fr[i].second;
+      sl++;
+    }
+    e->n_free_pad = (sl + 31) & ~31;
   }
   /* bins: components in order of their smallest voice, first-fit in order */
   std::vector<std::vector<int32_t>> members(roots.size());
@@ -399,14 +419,53 @@ static int replan(skb_engine *e, cudaStream_t st) {
   int slot = e->n_free_pad;
   e->n_free_rows = e->n_free_pad / 32;
   /* partial-row groups: one per (CTA, batch) of k_render_free, then the bins 16 to a group */
-  e->free_ctas = std::min(e->n_sm, e->n_free_rows);
-  e->free_groups = e->free_ctas ? e->free_ctas * (((e->n_free_rows + e->free_ctas - 1) / e->free_ctas + SKB_CTA_WARPS - 1) / SKB_CTA_WARPS) : 0;
-  e->n_groups = e->free_groups + ((int)binv.size() + SKB_CTA_WARPS - 1) / SKB_CTA_WARPS;
+  std::vector<int> ctarows;
+  {
+    /* Rows -> CTAs, balanced by estimated cost (LPT: costliest row first, to the least loaded
+     * CTA).  One CTA per SM; a CTA renders its rows in batches of SKB_CTA_WARPS, all rows of a
+     * batch concurrently, so its time is roughly (sum of row costs) / issue rate. */
+    static const int cost_of_rank[8] = {0, 20, 24, 29, 36, 36, 46, 160};   /* instructions per voice-frame, measured */
+    const int nrows = e->n_free_rows;
+    e->free_ctas = std::min(e->n_sm, nrows);
+    const int nb = e->free_ctas ? ((nrows + e->free_ctas - 1) / e->free_ctas + SKB_CTA_WARPS - 1) / SKB_CTA_WARPS : 0;
+    e->rows_cap = nb * SKB_CTA_WARPS;
+    e->free_groups = e->free_ctas * nb;
+    std::vector<std::pair<int, int>> rc((size_t)nrows);                    /* (cost, row) */
+    for (int r = 0; r < nrows; r++) {
+      int cost = 0;
+      for (int l = 0; l < 32 && !cost; l++) {
+        const int v = e->voice_of_slot[r * 32 + l];
+        if (v < 0) continue;
+        const uint64_t key = feature_key(&e->par[v]);
+        cost = cost_of_rank[(key >> SKB_KEY_CLASS_SHIFT) & 7];
+        if (e->par[v].flags & SKB_F_ONE_SHOT) cost = (cost + 3) / 4;      /* one-shots are mostly over; the kernel packs the rest */
+      }
+      rc[r] = std::make_pair(cost, r);
+    }
+    std::vector<std::pair<int, int>> order = rc;
+    std::stable_sort(order.begin(), order.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.first > b.first; });
+    typedef std::pair<long long, int> Load;                                /* (load, cta) */
+    std::priority_queue<Load, std::vector<Load>, std::greater<Load>> pqd;
+    for (int c = 0; c < e->free_ctas; c++) pqd.push(Load(0, c));
+    std::vector<std::vector<std::pair<int, int>>> mine((size_t)e->free_ctas);
+    for (size_t i = 0; i < order.size(); i++) {
+      Load l = pqd.top(); pqd.pop();
+      mine[l.second].push_back(order[i]);
+      l.first += order[i].first;
+      if ((int)mine[l.second].size() < e->rows_cap) pqd.push(l);          /* a full CTA leaves the heap */
+    }
+    ctarows.assign((size_t)std::max(e->free_ctas * e->rows_cap, 1), -1);
+    for (int c = 0; c < e->free_ctas; c++) {
+      std::sort(mine[c].begin(), mine[c].end());                          /* cheapest first: costliest = highest warp id */
+      for (size_t k = 0; k < mine[c].size(); k++) ctarows[(size_t)c * e->rows_cap + k] = mine[c][k].second;
+    }
+  }
+  e->n_prows = e->free_groups + (int)binv.size();
   e->max_bin_threads = 0;
   for (size_t b = 0; b < binv.size(); b++) {
     std::sort(binv[b].begin(), binv[b].end());
     skb_bin_desc d;
-    d.slot0 = slot; d.size = (int)binv[b].size(); d.nlevels = 1; d.row = e->free_groups * SKB_CTA_WARPS + (int)b;
+    d.slot0 = slot; d.size = (int)binv[b].size(); d.nlevels = 1; d.row = e->free_groups + (int)b;
     for (int i = 0; i < d.size; i++) {
       const int v = binv[b][i];
       e->slot_of_voice[v] = slot + i;
@@ -457,15 +516,16 @@ static int replan(skb_engine *e, cudaStream_t st) {
     CK(cudaStreamSynchronize(st));
   }
   {
-    /* rowcount: free groups are written by k_render_free each launch (0 until then), bin groups are static */
-    cudaError_t rr = grow_dev(&e->d_rowcount, &e->rowcount_cap, (size_t)std::max(e->n_groups, 1));
-    if (rr != cudaSuccess) return fail(e, SKB_ERR_CUDA, "rowcount alloc", cudaGetErrorString(rr));
+    cudaError_t rr;
+    rr = grow_dev(&e->d_ctarows, &e->ctarows_cap, ctarows.size());
+    if (rr != cudaSuccess) return fail(e, SKB_ERR_CUDA, "row list alloc", cudaGetErrorString(rr));
+    CK(cudaMemcpyAsync(e->d_ctarows, ctarows.data(), ctarows.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    e->h_ctarows = ctarows;
+    rr = grow_dev(&e->d_ctaphase, &e->ctaphase_cap, (size_t)std::max(e->free_ctas, 1) * 8);
+    if (rr != cudaSuccess) return fail(e, SKB_ERR_CUDA, "phase clock alloc", cudaGetErrorString(rr));
     rr = grow_dev(&e->d_envbuf, &e->envbuf_cap, (size_t)std::max(e->free_ctas, 1) * SKB_CTA_THREADS * SKB_ENV_WIN);
     if (rr != cudaSuccess) return fail(e, SKB_ERR_CUDA, "envelope scratch alloc", cudaGetErrorString(rr));
-    std::vector<int> rc((size_t)std::max(e->n_groups, 1), 0);
-    for (size_t b = 0; b < e->bins.size(); b++) rc[(size_t)e->free_groups + b / SKB_CTA_WARPS]++;
-    CK(cudaMemcpyAsync(e->d_rowcount, rc.data(), rc.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));
   }
   /* every owned voice gets a fresh record */
   std::fill(e->noise_flag.begin(), e->noise_flag.end(), 0);
@@ -600,7 +660,7 @@ int skb_render_mix(skb_engine *e, int nframes, uint64_t ssc_before, const float 
     CK(cudaMemcpyAsync(e->d_noise, e->h_noise, (size_t)nframes * sizeof(float), cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(e->ev_h2d, st));
   }
-  const size_t n_prow = (size_t)std::max(e->n_groups, 1) * SKB_CTA_WARPS;
+  const size_t n_prow = (size_t)std::max(e->n_prows, 1);
   if (n_prow * (size_t)e->cfg.max_frames > e->partials_cap) {
     CK(cudaStreamSynchronize(st));
     cudaError_t r = grow_dev(&e->d_partials, &e->partials_cap, n_prow * (size_t)e->cfg.max_frames);
@@ -609,9 +669,9 @@ int skb_render_mix(skb_engine *e, int nframes, uint64_t ssc_before, const float 
   CK(cudaEventRecord(e->ev_t0, st));
   if (e->n_free_rows > 0) {
     k_render_free<<<e->free_ctas, SKB_CTA_THREADS, skb_free_smem_bytes(), st>>>(
-                                                               e->d_pq, e->d_sq[e->cur], e->cap, e->n_free_rows, e->n_free,
+                                                               e->d_pq, e->d_sq[e->cur], e->cap, e->n_free_rows, e->n_free_pad, e->d_ctarows, e->rows_cap,
                                                                e->d_tables, e->d_noise, nframes, (unsigned long long)ssc_before,
-                                                               e->d_partials, nframes, e->d_rowcount, e->d_envbuf, e->d_counters,
+                                                               e->d_partials, nframes, e->d_envbuf, e->d_counters, e->d_ctaphase,
                                                                (e->cfg.flags & SKB_CFG_FORCE_GENERIC) ? 1 : 0);
     e->stats.kernel_launches++;
   }
@@ -623,10 +683,10 @@ int skb_render_mix(skb_engine *e, int nframes, uint64_t ssc_before, const float 
                                                          e->d_partials, nframes, e->d_counters + 1);
     e->stats.kernel_launches++;
   }
-  if (e->n_groups > 0) {
+  if (e->n_prows > 0) {
     dim3 blk(SKB_RED_X, SKB_RED_Y);
-    dim3 grd((nframes + SKB_RED_X - 1) / SKB_RED_X, std::max(1, std::min(SKB_RED_CHUNKS, e->n_groups / 2)));
-    k_reduce_rows<<<grd, blk, 0, st>>>(e->d_partials, e->d_rowcount, e->n_groups, nframes, nframes, e->d_part2,
+    dim3 grd((nframes + SKB_RED_X - 1) / SKB_RED_X, std::max(1, std::min(SKB_RED_CHUNKS, e->n_prows / 16)));
+    k_reduce_rows<<<grd, blk, 0, st>>>(e->d_partials, e->n_prows, nframes, nframes, e->d_part2,
                                        e->d_tickets, (float2 *)d_mix);
     e->stats.kernel_launches++;
   } else {
@@ -655,9 +715,12 @@ int skb_finish(skb_engine *e, const float *d_mix, int nframes, const float *gain
   k_finish<<<(nframes + 255) / 256, 256, 0, st>>>((const float2 *)d_mix, e->d_gain, e->d_out, nframes);
   e->stats.kernel_launches++;
   CK(cudaMemcpyAsync(e->h_out, e->d_out, (size_t)nframes * sizeof(float2), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(e->h_counters, e->d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(e->h_counters, e->d_counters, SKB_N_COUNTERS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   e->stats.active_voice_frames = e->h_counters[0] + e->h_counters[1];
+  for (int i = 0; i < 8; i++) e->stats.class_rows[i] = e->h_counters[2 + i];
+  for (int i = 0; i < 8; i++) e->stats.phase_cycles[i] = e->h_counters[10 + i];
+  e->stats.cta_batches = e->h_counters[18];
   if (num_channels == 2) {
     memcpy(out, e->h_out, (size_t)nframes * sizeof(float2));
   } else {
@@ -692,13 +755,18 @@ int skb_render(skb_engine *e, int nframes, uint64_t ssc_before, const float *gai
   return e->err;
 }
 
+float *skb_mix_buffer(skb_engine *e) { return e ? (float *)e->d_mix : nullptr; }
+
 int skb_sync(skb_engine *e, void *stream) {
   if (!e) return SKB_ERR_ARG;
   cudaSetDevice(e->cfg.device);
-  CK(cudaMemcpyAsync(e->h_counters, e->d_counters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+  CK(cudaMemcpyAsync(e->h_counters, e->d_counters, SKB_N_COUNTERS * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                      stream ? (cudaStream_t)stream : e->stream));
   CK(cudaStreamSynchronize(stream ? (cudaStream_t)stream : e->stream));
   e->stats.active_voice_frames = e->h_counters[0] + e->h_counters[1];
+  for (int i = 0; i < 8; i++) e->stats.class_rows[i] = e->h_counters[2 + i];
+  for (int i = 0; i < 8; i++) e->stats.phase_cycles[i] = e->h_counters[10 + i];
+  e->stats.cta_batches = e->h_counters[18];
   if (e->timing_pending) {
     float ms = 0.0f;
     if (cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1) == cudaSuccess) e->stats.last_render_ms = ms;
@@ -752,6 +820,29 @@ int skb_restore(skb_engine *e, int first, int n, const skb_voice_state *in) {
   e->stats.kernel_launches++;
   CK(cudaStreamSynchronize(st));
   return e->err;
+}
+
+/* Diagnostics: phase clocks (8 per CTA, SM cycles) of the last k_render_free launch and the
+ * planner's row list (rows_cap per CTA, -1 = none; row r = slots 32r..32r+31).  Returns the
+ * number of CTAs written (<= max_ctas). */
+int skb_debug_cta_phases(skb_engine *e, uint64_t *phases, int32_t *rows, int max_ctas, int *rows_cap) {
+  if (!e || !phases || max_ctas <= 0) return SKB_ERR_ARG;
+  cudaSetDevice(e->cfg.device);
+  const int n = std::min(max_ctas, e->free_ctas);
+  if (n <= 0 || !e->d_ctaphase) return 0;
+  CK(cudaStreamSynchronize(e->last_stream ? e->last_stream : e->stream));
+  CK(cudaMemcpy(phases, e->d_ctaphase, (size_t)n * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  if (rows_cap) *rows_cap = e->rows_cap;
+  if (rows) memcpy(rows, e->h_ctarows.data(), (size_t)n * e->rows_cap * sizeof(int32_t));
+  return n;
+}
+
+/* class rank (0 silent, 1..6 pipelined bodies by cost, 7 generic) of the voice in a slot, -1 = empty */
+int skb_debug_slot_rank(skb_engine *e, int slot) {
+  if (!e || slot < 0 || slot >= (int)e->voice_of_slot.size()) return -1;
+  const int v = e->voice_of_slot[slot];
+  if (v < 0) return -1;
+  return (int)((feature_key(&e->par[v]) >> SKB_KEY_CLASS_SHIFT) & 7) | ((e->par[v].flags & SKB_F_ONE_SHOT) ? 8 : 0);
 }
 
 int skb_get_stats(skb_engine *e, skb_stats *out) {

@@ -1038,13 +1038,6 @@ static int next_firing_boundary(int done, int num_frames, uint64_t start_count) 
   return num_frames + 1;
 }
 
-static void render_segment(float *buffer, int num_channels, int n) {
-  step_traces(n, 0);
-  int r = skb_render(g_engine, n, synth_sample_count, g_gain, g_noise, buffer, num_channels);
-  if (r != SKB_OK) shim_die("skb_render");
-  synth_sample_count += (uint64_t)n;
-}
-
 void synth(float *buffer, float *input, int num_frames, int num_channels, void *user) {
   (void)input; (void)user;   /* the per-voice tap `user` is opt-in: see skb_shim_* docs */
   static int first = 1;
@@ -1057,21 +1050,36 @@ void synth(float *buffer, float *input, int num_frames, int num_channels, void *
   mark_latency();
   const int EB = SYNTH_FRAMES_PER_CALLBACK;
   const uint64_t start_count = synth_sample_count;
+  float *d_mix = skb_mix_buffer(g_engine);
   int done = 0;
   while (done < num_frames) {
-    /* render up to the next boundary at which a queued event fires (everything
-     * in between is event-free, so one long launch equals many callbacks) */
-    int end = next_firing_boundary(done, num_frames, start_count);
-    const int fires = end <= num_frames;
-    if (!fires) end = num_frames;
-    if (end - done > g_cfg_max_frames) end = done + g_cfg_max_frames;
-    if (skb_shim_flush() != SKB_OK) shim_die("flush");
-    render_segment(buffer + (size_t)done * num_channels, num_channels, end - done);
-    if (fires && end - done > 0) {
-      const int sub = (end % EB) ? (end % EB) : EB;     /* length of the sub-block that just ended */
-      fire_due(sub);
+    /* one CHUNK of <= max_frames: its event-free segments are queued on the device back to
+     * back (the host fires the events of segment k+1 while the GPU renders segment k) and
+     * the chunk is finished — master volume, D2H, one synchronisation — at its end */
+    const int chunk0 = done;
+    const int chunk1 = (num_frames - done > g_cfg_max_frames) ? done + g_cfg_max_frames : num_frames;
+    g_gain_fill = 0;
+    while (done < chunk1) {
+      /* render up to the next boundary at which a queued event fires (everything in between
+       * is event-free, so one long launch equals many callbacks) */
+      int end = next_firing_boundary(done, num_frames, start_count);
+      const int fires = end <= chunk1;
+      if (!fires) end = chunk1;
+      if (skb_shim_flush() != SKB_OK) shim_die("flush");
+      const int n = end - done;
+      step_traces(n, 1);
+      if (skb_render_mix(g_engine, n, synth_sample_count, g_noise, d_mix + (size_t)(done - chunk0) * 2, NULL) != SKB_OK)
+        shim_die("skb_render_mix");
+      synth_sample_count += (uint64_t)n;
+      if (fires && n > 0) {
+        const int sub = (end % EB) ? (end % EB) : EB;     /* length of the sub-block that just ended */
+        fire_due(sub);
+      }
+      done = end;
     }
-    done = end;
+    if (skb_finish(g_engine, d_mix, chunk1 - chunk0, g_gain, buffer + (size_t)chunk0 * num_channels, num_channels, NULL) != SKB_OK)
+      shim_die("skb_finish");
+    g_gain_fill = 0;
   }
   clock_gettime(CLOCK_MONOTONIC, &g_bench[slot].b);
   g_bench[slot].state = 2;

@@ -393,53 +393,58 @@ k_render_bins(const float4 *__restrict__ pq, float4 *__restrict__ sq, int cap,
 /* ======================================================================== */
 /* K4  reduce_rows: partial rows -> raw stereo mix, fixed order              */
 /* ======================================================================== */
-/* Rows come in GROUPS of SKB_CTA_WARPS (one group per CTA batch of k_render_free, then the
- * modulation bins packed 16 to a group); rowcount[g] of them are valid.  Grid = frame tiles
- * of 32 x SKB_RED_CHUNKS group chunks, so that ~600 CTAs share the 8 B x rows x frames of
- * traffic instead of a handful.  Chunk c sums its groups in index order (y-strided, then
- * the 8 y partials in order) into part2[c][f]; the LAST chunk CTA of a frame tile to
- * arrive (atomic ticket) adds the chunk partials in chunk order — the result does not
- * depend on which CTA that is, so the sum is run-to-run deterministic. */
+/* One partial row per (CTA, batch) of k_render_free plus one per modulation bin.  Grid =
+ * frame tiles of 32 x row chunks.  Chunk c sums its rows in index order (y-strided, then the
+ * 8 y partials in order) into part2[c][f]; the LAST chunk CTA of a frame tile to arrive
+ * (atomic ticket) adds the chunk partials in chunk order — the result does not depend on
+ * which CTA that is, so the sum is run-to-run deterministic. */
 #define SKB_RED_X 32
 #define SKB_RED_Y 8
-#define SKB_RED_CHUNKS 32
+#define SKB_RED_CHUNKS 16
 __global__ void __launch_bounds__(SKB_RED_X * SKB_RED_Y)
-k_reduce_rows(const float2 *__restrict__ partials, const int *__restrict__ rowcount, int ngroups,
+k_reduce_rows(const float2 *__restrict__ partials, int nrows,
               int nframes, int row_stride, float2 *__restrict__ part2, unsigned int *__restrict__ tickets,
               float2 *__restrict__ mix) {
   __shared__ float2 acc[SKB_RED_Y][SKB_RED_X];
   __shared__ unsigned int s_ticket;
   const int f = blockIdx.x * SKB_RED_X + threadIdx.x;
   const int nch = gridDim.y, c = blockIdx.y;
-  const int per = (ngroups + nch - 1) / nch;
-  const int g0 = c * per, g1 = min(ngroups, g0 + per);
+  const int per = (nrows + nch - 1) / nch;
+  const int r0 = c * per, r1 = min(nrows, r0 + per);
   float L = 0.0f, R = 0.0f;
-  if (f < nframes)
-    for (int g = g0; g < g1; g++) {
-      const int nr = rowcount[g];
-      for (int r = threadIdx.y; r < nr; r += SKB_RED_Y) {
-        const float2 v = partials[(size_t)(g * SKB_CTA_WARPS + r) * row_stride + f];
-        L += v.x; R += v.y;
-      }
+  if (f < nframes) {
+#pragma unroll 4
+    for (int r = r0 + threadIdx.y; r < r1; r += SKB_RED_Y) {
+      const float2 v = partials[(size_t)r * row_stride + f];
+      L += v.x; R += v.y;
     }
+  }
   acc[threadIdx.y][threadIdx.x] = make_float2(L, R);
   __syncthreads();
   if (threadIdx.y == 0) {
+#pragma unroll
     for (int y = 1; y < SKB_RED_Y; y++) { L += acc[y][threadIdx.x].x; R += acc[y][threadIdx.x].y; }
-    if (f < nframes) part2[(size_t)c * row_stride + f] = make_float2(L, R);
-    __threadfence();
+    if (nch == 1) {
+      if (f < nframes) mix[f] = make_float2(L, R);
+    } else {
+      if (f < nframes) part2[(size_t)c * row_stride + f] = make_float2(L, R);
+      __threadfence();
+    }
   }
+  if (nch == 1) return;
   __syncthreads();
   if (threadIdx.x == 0 && threadIdx.y == 0) s_ticket = atomicAdd(&tickets[blockIdx.x], 1u);
   __syncthreads();
   if (s_ticket != (unsigned)(nch - 1)) return;
   __threadfence();
   if (threadIdx.y == 0 && f < nframes) {
+    float2 v[SKB_RED_CHUNKS];
+#pragma unroll
+    for (int i = 0; i < SKB_RED_CHUNKS; i++)
+      v[i] = (i < nch) ? __ldcg(&part2[(size_t)i * row_stride + f]) : make_float2(0.0f, 0.0f);
     float l = 0.0f, r = 0.0f;
-    for (int i = 0; i < nch; i++) {
-      const float2 v = __ldcg(&part2[(size_t)i * row_stride + f]);
-      l += v.x; r += v.y;
-    }
+#pragma unroll
+    for (int i = 0; i < SKB_RED_CHUNKS; i++) if (i < nch) { l += v[i].x; r += v[i].y; }
     mix[f] = make_float2(l, r);
   }
   if (threadIdx.x == 0 && threadIdx.y == 0) tickets[blockIdx.x] = 0u;     /* ready for the next launch */

@@ -22,7 +22,8 @@ class NativeLibraryMissing(RuntimeError):
 
 
 def engine_lib_path():
-    return os.path.join(HERE, "libskred_b200.so")
+    # SKB_ENGINE_LIB: an alternative build of the same engine (tuning experiments, tools/)
+    return os.environ.get("SKB_ENGINE_LIB") or os.path.join(HERE, "libskred_b200.so")
 
 
 def shim_lib_path(voice_max):
@@ -81,7 +82,8 @@ class skb_stats(C.Structure):
                 ("ops_applied", C.c_uint64), ("params_uploaded", C.c_uint64), ("replans", C.c_uint64),
                 ("n_free_voices", C.c_int32), ("n_group_voices", C.c_int32), ("n_groups", C.c_int32),
                 ("n_owned_voices", C.c_int32), ("last_render_ms", C.c_float), ("_pad", C.c_int32),
-                ("active_voice_frames", C.c_uint64)]
+                ("active_voice_frames", C.c_uint64), ("class_rows", C.c_uint64 * 8),
+                ("phase_cycles", C.c_uint64 * 8), ("cta_batches", C.c_uint64)]
 
 
 class SynthAPI:

@@ -101,8 +101,10 @@ def test_big_callbacks_equal_small_callbacks(luts):
 
 @pytest.mark.parametrize("name", ["lut_adsr", "korg_cz_filter", "pcm_retrigger", "misc"])
 def test_specialised_path_equals_generic_path(name, luts, monkeypatch):
-    """The warp-specialised fast path and the generic per-frame path of k_render_free
-    must produce identical bits (same ops on the same operands, only hoisted)."""
+    """The pipelined path and the generic per-frame path of k_render_free must leave identical
+    bits in every evolving word of every voice (same ops on the same operands, only hoisted).
+    The mix is compared within the float budget: the two runs pack different warps, which
+    regroups the cross-voice sum."""
     wl = cases.SYNTHETIC[name](luts)
     a = O.DropinCuda(wl["voices"])
     cases.drive_setup(a, wl)
@@ -111,7 +113,7 @@ def test_specialised_path_equals_generic_path(name, luts, monkeypatch):
     b = O.DropinCuda(wl["voices"])
     cases.drive_setup(b, wl)
     ob = cases.drive_render(b, wl)
-    assert np.array_equal(oa.view(np.uint32), ob.view(np.uint32))
+    assert maxdiff(oa, ob) <= 1e-6
     assert_state_equal(a.state(), b.state())
 
 
@@ -148,8 +150,10 @@ def test_config5_stationary_1024_vs_reference(luts):
 
 
 def test_long_launch_equals_callbacks_with_envelopes_and_one_shots(luts):
-    """One synth() call of 8,192 frames (16 envelope windows inside one launch, one-shots ending
-    inside it) equals 16 callbacks of 512, bit for bit."""
+    """One synth() call of 8,492 frames (17 envelope windows inside one launch, one-shots ending
+    inside it) against 17 callbacks: every evolving word of every voice bit-identical.  The mix is
+    compared within the float budget only: a voice that ended is dropped from the warps at the
+    next launch, which regroups the (fixed-order, but launch-dependent) cross-voice sum."""
     from skred_b200 import workloads as W
     wl = W.config5(1024, seconds=600.0, luts=luts, event_seconds=0.0, stationary=True)
     a, b = O.DropinCuda(1024, run_seq=False), O.DropinCuda(1024, run_seq=False)
@@ -157,5 +161,5 @@ def test_long_launch_equals_callbacks_with_envelopes_and_one_shots(luts):
         W.install(s, wl)
     oa = a.render(8192 + 300, block=512)
     ob = b.render(8192 + 300, block=8192 + 300)
-    assert np.array_equal(oa.view(np.uint32), ob.view(np.uint32))
+    assert maxdiff(oa, ob) <= 1e-7
     assert_state_equal(a.state(), b.state())

@@ -52,6 +52,10 @@ for name, fn in CLASSES.items():
         sk.lib.synth(out.ctypes.data, None, F, 2, None)
         ms.append(sk.stats().last_render_ms)
     vs = V * F
+    st_ = sk.stats()
+    print("   phase us/CTA-pass [compact setup tables prepass render wait rowsum store]:",
+          ["%.1f" % (x / max(st_.cta_batches, 1) / 1965.0) for x in st_.phase_cycles])
+    print("   rows per class (none, none+f, pw, pw+f, pow, pow+f, mixed, generic):", list(sk.stats().class_rows))
     print("%-22s kernel ms: first %.3f  decay %.3f  sustain %.3f   -> %.3g voice-samples/s (sustain)" %
           (name, ms[0], ms[5], ms[-1], vs / (ms[-1] * 1e-3)), flush=True)
     sk.lib.synth_free()
