@@ -231,8 +231,12 @@ def own_arm(a):
     st0 = sk.stats()
     owned = st0.n_owned_voices if world > 1 else V
 
-    stream = torch.cuda.current_stream()
+    # a real stream: the legacy default stream's handle is 0, which the engine reads as "use your own",
+    # and then neither the CUDA events below nor NCCL would be ordered with the kernels
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     sp = C.c_void_p(stream.cuda_stream)
+    assert sp.value
     d_mix = torch.zeros((F, 2), dtype=torch.float32, device="cuda")
     out = np.zeros((F, 2), dtype=np.float32)
 

@@ -28,8 +28,12 @@ class ShardedRenderer:
         self.block = block
         self._mix = None
         self.stream = None
+        self.tstream = None
         if device != "cpu":
-            self.stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            # a real stream of our own: the engine's kernels and the NCCL reduce are ordered on it
+            # (the legacy default stream has handle 0, which the engine reads as "use your own stream")
+            self.tstream = torch.cuda.Stream()
+            self.stream = C.c_void_p(self.tstream.cuda_stream)
 
     def _buffer(self, frames):
         if self._mix is None or self._mix.shape[0] < frames:
@@ -45,7 +49,11 @@ class ShardedRenderer:
             n = min(lf, frames - b)
             self.api.render_mix(n, ptr + b * 8, self.stream)
         if self.dist:
-            self.dist.reduce(mix, dst=0, op=self.dist.ReduceOp.SUM)
+            if self.tstream is not None:
+                with self.torch.cuda.stream(self.tstream):
+                    self.dist.reduce(mix, dst=0, op=self.dist.ReduceOp.SUM)
+            else:
+                self.dist.reduce(mix, dst=0, op=self.dist.ReduceOp.SUM)
         return mix
 
     def render(self, frames, out=None, launch_frames=None):
