@@ -244,8 +244,11 @@ def own_arm(a):
     mix_ptr = d_mix.data_ptr()
 
     def render_step():
+        # one callback-sized segment per call, like a host's audio callback; the engine batches the
+        # calls of a step into one launch and applies the events at the 512-frame boundaries itself
         for b in range(0, F, LF):
             sk.render_mix(LF, mix_ptr + b * 8, sp)
+        sk.lib.skb_shim_flush_render()
 
     def step_device():
         render_step()
@@ -308,7 +311,7 @@ def own_arm(a):
         eng.skb_sync(sk.engine, sp)
         st_k = sk.stats()
         kern_ms.append(st_k.last_render_ms)
-        kern_active.append((st_k.active_voice_frames - a_b) / (F // LF))      # per launch
+        kern_active.append(st_k.active_voice_frames - a_b)                    # per launch (one batched launch per step)
     barrier()
     sk.lib.skb_shim_discard_gain()
 
@@ -347,8 +350,8 @@ def own_arm(a):
     k_act = float(np.mean(kern_active))
     # launch traffic: every owned voice's amp + first state group are read (32 B) to decide the skip;
     # a rendered voice moves its full 276 B record
-    alive_per_launch = k_act / LF
-    algo_bytes = alive_per_launch * BYTES_PER_VOICE_LAUNCH + (owned - alive_per_launch) * 32.0 + LF * 8
+    alive_per_launch = k_act / F
+    algo_bytes = alive_per_launch * BYTES_PER_VOICE_LAUNCH + (owned - alive_per_launch) * 32.0 + F * 8
     ach_gbs = algo_bytes / (k_ms * 1e-3) / 1e9
     fp32_peak = N_SM * FP32_LANES_PER_SM * sm_mhz * 1e6
     # config 5 by v%3: LUT (15 ops) and Korg+CZ+biquad (32 ops) voices always render; the one-shot PCM third (15 ops)
@@ -363,11 +366,12 @@ def own_arm(a):
             "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD % V,
-                       "voices": V, "frames_per_step": F, "frames_per_launch": LF, "block_frames": 512,
+                       "voices": V, "frames_per_step": F, "frames_per_call": LF, "frames_per_launch": F, "block_frames": 512,
                        "active_fraction": act_dev / (V * F * a.steps),
                        "counting": "rendered voice-frames only: voices skipped by synth.c:531-542 (finished one-shots) do not count",
                        "value_counting_all_voice_slots": V * F * a.steps / (dev_ms * 1e-3),
                        "parallelism": "voice-sharded x%d, NCCL reduce of stereo partials" % world if world > 1 else "1 GPU",
+                       "launches": "the engine renders the %d callbacks of a step in one launch; events are applied in-kernel at the 512-frame boundaries" % (F // LF),
                        "l2": "state+params %.1f MB per launch, each word touched once per launch (no reuse to cache)" % (owned * 276 / 1e6)},
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                          "traffic": None, "peak_kind": peak_kind, "kernel": "k_render_free(+k_render_bins,+k_reduce_rows)",

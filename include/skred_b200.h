@@ -152,6 +152,8 @@ typedef struct skb_config {
 /* testing aid: render every free voice through the generic per-frame code path
  * instead of the warp-specialised one (both must produce identical bits) */
 #define SKB_CFG_FORCE_GENERIC 1u
+/* testing aid: one launch per skb_render_mix call (no batching of consecutive callbacks) */
+#define SKB_CFG_NO_BATCH 2u
 
 int  skb_create(skb_engine **out, const skb_config *cfg);
 void skb_destroy(skb_engine *e);
@@ -195,6 +197,13 @@ int  skb_render(skb_engine *e, int nframes, uint64_t ssc_before,
  * call skb_finish on the root to apply `gain` and copy to the host. */
 int  skb_render_mix(skb_engine *e, int nframes, uint64_t ssc_before,
                     const float *noise, float *d_mix, void *stream);
+/* skb_render_mix may DEFER its launch: consecutive calls that continue each other (next frames,
+ * next d_mix address, same stream) and are separated only by state edits (skb_push_ops) are
+ * rendered by ONE kernel launch that applies those edits itself at the callback boundaries.
+ * skb_flush launches what is pending (no host synchronisation); skb_finish / skb_sync /
+ * skb_snapshot do so implicitly.  Call it before consuming d_mix on the stream yourself
+ * (e.g. before an NCCL reduce). */
+int  skb_flush(skb_engine *e);
 int  skb_finish(skb_engine *e, const float *d_mix, int nframes, const float *gain,
                 float *out, int num_channels, void *stream);
 /* The engine's own raw-mix buffer (DEVICE memory, max_frames x 2 floats) for callers of the

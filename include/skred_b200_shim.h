@@ -89,6 +89,9 @@ void skb_shim_wave_touch(int wave);
  * volume of synth.c:616-620) on `stream`; after the partial mixes were summed
  * across GPUs (ncclReduce over NVLink) the root calls skb_shim_finish. */
 int  skb_shim_render_mix(int num_frames, float *d_mix, void *stream);
+/* The engine batches consecutive skb_shim_render_mix calls into one launch (skb_flush in
+ * skred_b200.h): launch what is pending before touching d_mix on the stream yourself. */
+int  skb_shim_flush_render(void);
 int  skb_shim_finish(const float *d_mix, int num_frames, float *out, int num_channels, void *stream);
 /* A non-root rank (or a caller that keeps the raw mix on the device) drops the
  * master-volume trace accumulated by its skb_shim_render_mix calls. */

@@ -407,6 +407,7 @@ int skb_render(skb_engine *e, int nframes, uint64_t ssc, const float *gain, cons
 int skb_sync(skb_engine *e, void *stream) { (void)stream; return e ? e->err : SKB_ERR_ARG; }
 
 float *skb_mix_buffer(skb_engine *e) { return e ? e->mix : NULL; }
+int skb_flush(skb_engine *e) { return e ? e->err : SKB_ERR_ARG; }      /* the port renders synchronously */
 
 /* no kernels, no phases */
 int skb_debug_cta_phases(skb_engine *e, uint64_t *phases, int32_t *rows, int max_ctas, int *rows_cap) {

@@ -97,9 +97,28 @@ struct skb_engine {
 
   std::vector<skb_op> ops;
   skb_stats stats;
+
+  /* pending batch of consecutive callbacks: rendered by ONE launch of k_render_free */
+  struct {
+    bool open = false;
+    cudaStream_t st = nullptr;
+    float *mix = nullptr;               /* device, batch frames x 2 */
+    int frames = 0;
+    uint64_t ssc0 = 0;
+    std::vector<int> win_frames;        /* each <= SKB_ENV_WIN */
+    std::vector<int> win_ob;            /* ops applied before window w start at ops[win_ob[w]] */
+    std::vector<skb_op> ops;            /* op.voice = slot */
+    std::vector<uint32_t> wake;         /* bit per slot touched by an op of the batch */
+    std::vector<int> wake_words;        /* ... and which words are non-zero */
+  } batch;
+  int *d_win = nullptr, *h_win = nullptr; size_t win_cap = 0, h_win_cap = 0;
+  skb_op *d_bops = nullptr, *h_bops = nullptr; size_t bops_cap = 0, h_bops_cap = 0;
+  uint32_t *d_wake = nullptr, *h_wake = nullptr; size_t wake_cap = 0, h_wake_cap = 0;
 };
 
 const char *skb_backend_name(void) { return "cuda-sm100a"; }
+
+static int batch_launch(skb_engine *e);
 
 static int fail(skb_engine *e, int code, const char *what, const char *detail = nullptr) {
   if (e && e->err == SKB_OK) {
@@ -213,12 +232,15 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
 void skb_destroy(skb_engine *e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
+  batch_launch(e);
   if (e->stream) cudaStreamSynchronize(e->stream);
   cudaFree(e->d_pq); cudaFree(e->d_sq[0]); cudaFree(e->d_sq[1]); cudaFree(e->d_tables);
   cudaFree(e->d_bins); cudaFree(e->d_partials); cudaFree(e->d_mix); cudaFree(e->d_out);
   cudaFree(e->d_gain); cudaFree(e->d_noise); cudaFree(e->d_idx); cudaFree(e->d_recs);
   cudaFree(e->d_ops); cudaFree(e->d_runs); cudaFree(e->d_snap);
   cudaFree(e->d_envbuf); cudaFree(e->d_ctarows); cudaFree(e->d_ctaphase);
+  cudaFree(e->d_win); cudaFree(e->d_bops); cudaFree(e->d_wake);
+  cudaFreeHost(e->h_win); cudaFreeHost(e->h_bops); cudaFreeHost(e->h_wake);
   cudaFree(e->d_part2); cudaFree(e->d_tickets); cudaFree(e->d_counters);
   cudaFreeHost(e->h_counters);
   cudaFreeHost(e->h_gain); cudaFreeHost(e->h_noise); cudaFreeHost(e->h_out); cudaFreeHost(e->h_idx);
@@ -236,9 +258,10 @@ const char *skb_error_string(const skb_engine *e) { return e ? e->errtxt : "null
 int skb_table_upload(skb_engine *e, const float *data, int size) {
   if (!e || !data || size <= 0) return fail(e, SKB_ERR_ARG, "table_upload: bad argument");
   cudaSetDevice(e->cfg.device);
+  if (batch_launch(e)) return e->err;
   const size_t need = e->tables_used + (size_t)((size + 31) & ~31);   /* 128-byte aligned starts */
-  if (need + SKB_TBL_CHUNK > e->tables_cap) {               /* slack: the table cache copies whole chunks */
-    size_t ncap = std::max(need + SKB_TBL_CHUNK, e->tables_cap * 2);
+  if (need > e->tables_cap) {
+    size_t ncap = std::max(need, e->tables_cap * 2);
     float *nt = nullptr;
     CK(cudaMalloc((void **)&nt, ncap * sizeof(float)));
     CK(cudaStreamSynchronize(e->last_stream ? e->last_stream : e->stream));
@@ -640,8 +663,91 @@ int skb_owns_voice(skb_engine *e, int voice) {
   if (!e || voice < 0 || voice >= e->n) return 0;
   if (e->cfg.world == 1) return 1;
   cudaSetDevice(e->cfg.device);
+  if (batch_launch(e)) return 0;
   if (use_stream(e, e->stream) || sync_inputs(e, e->stream)) return 0;
   return e->owner[voice] == e->cfg.rank;
+}
+
+/* Launch the pending batch (no host synchronisation). */
+static int batch_launch(skb_engine *e) {
+  if (!e->batch.open) return e->err;
+  e->batch.open = false;
+  const int nframes = e->batch.frames;
+  if (nframes == 0) return e->err;
+  cudaStream_t st = e->batch.st;
+  const int nwin = (int)e->batch.win_frames.size();
+  const size_t nops = e->batch.ops.size();
+  e->batch.win_ob.push_back((int)nops);                       /* CSR sentinel */
+  cudaError_t r;
+  if (wait_staging(e)) return e->err;
+  const size_t nwi = (size_t)2 * nwin + 1;
+  if ((r = grow_pin(&e->h_win, &e->h_win_cap, nwi)) != cudaSuccess || (r = grow_dev(&e->d_win, &e->win_cap, nwi)) != cudaSuccess)
+    return fail(e, SKB_ERR_CUDA, "window list alloc", cudaGetErrorString(r));
+  memcpy(e->h_win, e->batch.win_frames.data(), (size_t)nwin * sizeof(int));
+  memcpy(e->h_win + nwin, e->batch.win_ob.data(), (size_t)(nwin + 1) * sizeof(int));
+  CK(cudaMemcpyAsync(e->d_win, e->h_win, nwi * sizeof(int), cudaMemcpyHostToDevice, st));
+  const unsigned *d_wake = nullptr;
+  if (nops) {
+    const size_t nw = ((size_t)e->cap + 31) / 32;
+    if ((r = grow_pin(&e->h_bops, &e->h_bops_cap, nops)) != cudaSuccess || (r = grow_dev(&e->d_bops, &e->bops_cap, nops)) != cudaSuccess ||
+        (r = grow_pin(&e->h_wake, &e->h_wake_cap, nw)) != cudaSuccess || (r = grow_dev(&e->d_wake, &e->wake_cap, nw)) != cudaSuccess)
+      return fail(e, SKB_ERR_CUDA, "batch op alloc", cudaGetErrorString(r));
+    memcpy(e->h_bops, e->batch.ops.data(), nops * sizeof(skb_op));
+    memcpy(e->h_wake, e->batch.wake.data(), nw * sizeof(uint32_t));
+    CK(cudaMemcpyAsync(e->d_bops, e->h_bops, nops * sizeof(skb_op), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->d_wake, e->h_wake, nw * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    d_wake = e->d_wake;
+    for (size_t i = 0; i < e->batch.wake_words.size(); i++) e->batch.wake[e->batch.wake_words[i]] = 0u;
+    e->batch.wake_words.clear();
+  }
+  if (e->any_noise)
+    CK(cudaMemcpyAsync(e->d_noise, e->h_noise, (size_t)nframes * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(e->ev_h2d, st));
+  const size_t n_prow = (size_t)std::max(e->n_prows, 1);
+  if (n_prow * (size_t)e->cfg.max_frames > e->partials_cap) {
+    CK(cudaStreamSynchronize(st));
+    r = grow_dev(&e->d_partials, &e->partials_cap, n_prow * (size_t)e->cfg.max_frames);
+    if (r != cudaSuccess) return fail(e, SKB_ERR_CUDA, "partials alloc", cudaGetErrorString(r));
+  }
+  CK(cudaEventRecord(e->ev_t0, st));
+  if (e->n_free_rows > 0) {
+    k_render_free<<<e->free_ctas, SKB_CTA_THREADS, skb_free_smem_bytes(), st>>>(
+        e->d_pq, e->d_sq[e->cur], e->cap, e->n_free_rows, e->n_free_pad, e->d_ctarows, e->rows_cap,
+        e->d_tables, e->d_noise, nframes, (unsigned long long)e->batch.ssc0,
+        e->d_win, e->d_win + nwin, nwin, e->d_bops, d_wake,
+        e->d_partials, nframes, e->d_envbuf, e->d_counters, e->d_ctaphase,
+        (e->cfg.flags & SKB_CFG_FORCE_GENERIC) ? 1 : 0);
+    e->stats.kernel_launches++;
+  }
+  if (!e->bins.empty()) {                                     /* (a batch with bins is always one segment without in-kernel ops) */
+    const int nt = e->max_bin_threads;
+    const size_t smem = (size_t)3 * nt * sizeof(float) + (size_t)2 * (nt / 32) * sizeof(float2);
+    k_render_bins<<<(int)e->bins.size(), nt, smem, st>>>(e->d_pq, e->d_sq[e->cur], e->cap, e->d_bins, e->d_tables,
+                                                         e->d_noise, nframes, (unsigned long long)e->batch.ssc0,
+                                                         e->d_partials, nframes, e->d_counters + 1);
+    e->stats.kernel_launches++;
+  }
+  if (e->n_prows > 0) {
+    dim3 blk(SKB_RED_X, SKB_RED_Y);
+    dim3 grd((nframes + SKB_RED_X - 1) / SKB_RED_X, std::max(1, std::min(SKB_RED_CHUNKS, e->n_prows / 16)));
+    k_reduce_rows<<<grd, blk, 0, st>>>(e->d_partials, e->n_prows, nframes, nframes, e->d_part2,
+                                       e->d_tickets, (float2 *)e->batch.mix);
+    e->stats.kernel_launches++;
+  } else {
+    CK(cudaMemsetAsync(e->batch.mix, 0, (size_t)nframes * sizeof(float2), st));
+  }
+  CK(cudaEventRecord(e->ev_t1, st));
+  e->timing_pending = true;
+  CK(cudaGetLastError());
+  e->batch.frames = 0;
+  e->batch.win_frames.clear(); e->batch.win_ob.clear(); e->batch.ops.clear();
+  return e->err;
+}
+
+int skb_flush(skb_engine *e) {
+  if (!e) return SKB_ERR_ARG;
+  cudaSetDevice(e->cfg.device);
+  return batch_launch(e);
 }
 
 int skb_render_mix(skb_engine *e, int nframes, uint64_t ssc_before, const float *noise,
@@ -650,52 +756,55 @@ int skb_render_mix(skb_engine *e, int nframes, uint64_t ssc_before, const float 
   if (nframes < 0 || nframes > e->cfg.max_frames || !d_mix) return fail(e, SKB_ERR_ARG, "render_mix: bad argument");
   cudaSetDevice(e->cfg.device);
   cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
-  if (use_stream(e, st)) return e->err;
-  if (sync_inputs(e, st)) return e->err;
-  if (nframes == 0) return e->err;
+  if (e->err) return e->err;
+  /* Can this segment ride in the pending launch?  Yes if it continues it (same stream, next
+   * frames, next mix address), fits, and everything the host queued since is a pure state edit
+   * (ops): those are applied by the kernel itself at the window boundary.  Parameter changes,
+   * re-plans and modulation bins end the batch. */
+  bool extend = e->batch.open && e->batch.st == st && e->batch.mix + (size_t)e->batch.frames * 2 == d_mix &&
+                e->batch.ssc0 + (uint64_t)e->batch.frames == ssc_before &&
+                e->batch.frames + nframes <= e->cfg.max_frames && e->bins.empty() && e->planned && !e->need_plan &&
+                e->dirty_list.empty() && !(e->cfg.flags & SKB_CFG_NO_BATCH);
+  if (extend && !e->ops.empty() && e->batch.frames % SKB_ENV_WIN != 0) extend = false;   /* (boundaries are window starts) */
+  if (!extend) {
+    if (batch_launch(e)) return e->err;
+    if (use_stream(e, st)) return e->err;
+    if (sync_inputs(e, st)) return e->err;        /* plan, parameter records, ops -> k_apply_ops */
+    if (nframes == 0) return e->err;
+    e->batch.open = true; e->batch.st = st; e->batch.mix = d_mix; e->batch.frames = 0; e->batch.ssc0 = ssc_before;
+    e->batch.win_frames.clear(); e->batch.win_ob.clear(); e->batch.ops.clear();
+    if (e->batch.wake.size() < ((size_t)e->cap + 31) / 32) e->batch.wake.assign(((size_t)e->cap + 31) / 32, 0u);
+  } else if (nframes == 0) {
+    return e->err;
+  }
   if (e->any_noise) {
     if (!noise) return fail(e, SKB_ERR_ARG, "render_mix: a voice uses the shared noise source but noise == NULL");
-    if (wait_staging(e)) return e->err;
-    memcpy(e->h_noise, noise, (size_t)nframes * sizeof(float));
-    CK(cudaMemcpyAsync(e->d_noise, e->h_noise, (size_t)nframes * sizeof(float), cudaMemcpyHostToDevice, st));
-    CK(cudaEventRecord(e->ev_h2d, st));
+    if (e->batch.frames == 0 && wait_staging(e)) return e->err;
+    memcpy(e->h_noise + e->batch.frames, noise, (size_t)nframes * sizeof(float));
   }
-  const size_t n_prow = (size_t)std::max(e->n_prows, 1);
-  if (n_prow * (size_t)e->cfg.max_frames > e->partials_cap) {
-    CK(cudaStreamSynchronize(st));
-    cudaError_t r = grow_dev(&e->d_partials, &e->partials_cap, n_prow * (size_t)e->cfg.max_frames);
-    if (r != cudaSuccess) return fail(e, SKB_ERR_CUDA, "partials alloc", cudaGetErrorString(r));
+  /* this segment's windows; the queued ops belong to the boundary before its first window */
+  e->batch.win_ob.push_back((int)e->batch.ops.size());
+  if (extend && !e->ops.empty()) {
+    for (size_t i = 0; i < e->ops.size(); i++) {
+      skb_op op = e->ops[i];
+      const int v = op.voice;
+      if (v < 0 || v >= e->n || e->slot_of_voice[v] < 0) continue;
+      op.voice = e->slot_of_voice[v];
+      e->batch.ops.push_back(op);
+      const int w = op.voice >> 5;
+      if (!e->batch.wake[w]) e->batch.wake_words.push_back(w);
+      e->batch.wake[w] |= 1u << (op.voice & 31);
+    }
+    e->stats.ops_applied += e->ops.size();
+    e->ops.clear();
   }
-  CK(cudaEventRecord(e->ev_t0, st));
-  if (e->n_free_rows > 0) {
-    k_render_free<<<e->free_ctas, SKB_CTA_THREADS, skb_free_smem_bytes(), st>>>(
-                                                               e->d_pq, e->d_sq[e->cur], e->cap, e->n_free_rows, e->n_free_pad, e->d_ctarows, e->rows_cap,
-                                                               e->d_tables, e->d_noise, nframes, (unsigned long long)ssc_before,
-                                                               e->d_partials, nframes, e->d_envbuf, e->d_counters, e->d_ctaphase,
-                                                               (e->cfg.flags & SKB_CFG_FORCE_GENERIC) ? 1 : 0);
-    e->stats.kernel_launches++;
+  for (int done = 0; done < nframes; done += SKB_ENV_WIN) {
+    if (done) e->batch.win_ob.push_back((int)e->batch.ops.size());
+    e->batch.win_frames.push_back(std::min(SKB_ENV_WIN, nframes - done));
   }
-  if (!e->bins.empty()) {
-    const int nt = e->max_bin_threads;
-    const size_t smem = (size_t)3 * nt * sizeof(float) + (size_t)2 * (nt / 32) * sizeof(float2);
-    k_render_bins<<<(int)e->bins.size(), nt, smem, st>>>(e->d_pq, e->d_sq[e->cur], e->cap, e->d_bins, e->d_tables,
-                                                         e->d_noise, nframes, (unsigned long long)ssc_before,
-                                                         e->d_partials, nframes, e->d_counters + 1);
-    e->stats.kernel_launches++;
-  }
-  if (e->n_prows > 0) {
-    dim3 blk(SKB_RED_X, SKB_RED_Y);
-    dim3 grd((nframes + SKB_RED_X - 1) / SKB_RED_X, std::max(1, std::min(SKB_RED_CHUNKS, e->n_prows / 16)));
-    k_reduce_rows<<<grd, blk, 0, st>>>(e->d_partials, e->n_prows, nframes, nframes, e->d_part2,
-                                       e->d_tickets, (float2 *)d_mix);
-    e->stats.kernel_launches++;
-  } else {
-    CK(cudaMemsetAsync(d_mix, 0, (size_t)nframes * sizeof(float2), st));
-  }
-  CK(cudaEventRecord(e->ev_t1, st));
-  e->timing_pending = true;
-  CK(cudaGetLastError());
+  e->batch.frames += nframes;
   e->stats.frames_rendered += (uint64_t)nframes;
+  if (!e->bins.empty() || (e->cfg.flags & SKB_CFG_NO_BATCH)) return batch_launch(e);
   return e->err;
 }
 
@@ -707,6 +816,7 @@ int skb_finish(skb_engine *e, const float *d_mix, int nframes, const float *gain
   if (nframes == 0) return e->err;
   cudaSetDevice(e->cfg.device);
   cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  if (batch_launch(e)) return e->err;
   if (use_stream(e, st)) return e->err;
   if (wait_staging(e)) return e->err;
   memcpy(e->h_gain, gain, (size_t)nframes * sizeof(float));
@@ -760,6 +870,7 @@ float *skb_mix_buffer(skb_engine *e) { return e ? (float *)e->d_mix : nullptr; }
 int skb_sync(skb_engine *e, void *stream) {
   if (!e) return SKB_ERR_ARG;
   cudaSetDevice(e->cfg.device);
+  if (batch_launch(e)) return e->err;
   CK(cudaMemcpyAsync(e->h_counters, e->d_counters, SKB_N_COUNTERS * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                      stream ? (cudaStream_t)stream : e->stream));
   CK(cudaStreamSynchronize(stream ? (cudaStream_t)stream : e->stream));
@@ -793,6 +904,7 @@ int skb_snapshot(skb_engine *e, int first, int n, skb_voice_state *out) {
   if (n == 0) return e->err;
   cudaSetDevice(e->cfg.device);
   cudaStream_t st = e->stream;
+  if (batch_launch(e)) return e->err;
   if (use_stream(e, st)) return e->err;
   if (sync_inputs(e, st)) return e->err;
   if (stage_slots(e, first, n)) return e->err;
@@ -810,6 +922,7 @@ int skb_restore(skb_engine *e, int first, int n, const skb_voice_state *in) {
   if (n == 0) return e->err;
   cudaSetDevice(e->cfg.device);
   cudaStream_t st = e->stream;
+  if (batch_launch(e)) return e->err;
   if (use_stream(e, st)) return e->err;
   if (sync_inputs(e, st)) return e->err;
   if (stage_slots(e, first, n)) return e->err;
@@ -830,6 +943,7 @@ int skb_debug_cta_phases(skb_engine *e, uint64_t *phases, int32_t *rows, int max
   cudaSetDevice(e->cfg.device);
   const int n = std::min(max_ctas, e->free_ctas);
   if (n <= 0 || !e->d_ctaphase) return 0;
+  if (batch_launch(e)) return e->err;
   CK(cudaStreamSynchronize(e->last_stream ? e->last_stream : e->stream));
   CK(cudaMemcpy(phases, e->d_ctaphase, (size_t)n * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   if (rows_cap) *rows_cap = e->rows_cap;

@@ -123,6 +123,7 @@ static skb_engine *engine(void) {
   cfg.rank = g_cfg_rank;
   cfg.world = g_cfg_world;
   if ((s = getenv("SKB_FORCE_GENERIC")) && atoi(s)) cfg.flags |= SKB_CFG_FORCE_GENERIC;
+  if ((s = getenv("SKB_NO_BATCH")) && atoi(s)) cfg.flags |= SKB_CFG_NO_BATCH;
   int r = skb_create(&g_engine, &cfg);
   if (r != SKB_OK || !g_engine) {
     fprintf(stderr, "skred_b200: FATAL: cannot create %s engine (error %d); there is no CPU fallback\n",
@@ -1104,6 +1105,9 @@ int skb_shim_render_mix(int num_frames, float *d_mix, void *stream) {
 }
 
 void skb_shim_discard_gain(void) { g_gain_fill = 0; }
+
+/* launch whatever skb_shim_render_mix deferred (before the caller consumes d_mix on its stream) */
+int skb_shim_flush_render(void) { return skb_flush(engine()); }
 
 int skb_shim_finish(const float *d_mix, int num_frames, float *out, int num_channels, void *stream) {
   /* consumes the gain trace of every skb_shim_render_mix since the last finish */

@@ -300,6 +300,25 @@ __device__ __forceinline__ float2 voice_frame(const VoiceP &p, const VoiceK &k, 
   return make_float2(out * s.panL, out * s.panR);                                 /* :603-604 */
 }
 
+/* ops are sorted (stably) by slot on the host; one thread replays one slot's
+ * run in order.  op.voice holds the SLOT here. */
+__device__ __forceinline__ void dev_apply_op(VoiceS &s, const skb_op &op) {
+  switch (op.code) {
+    case SKB_OP_TRIGGER:      s.finished = 0; s.phase = op.f0; break;                       /* synth.c:316-339 */
+    case SKB_OP_SET_FINISHED: s.finished = op.i0; break;                                    /* synth.c:281-282 */
+    case SKB_OP_ENV_ON:       s.env_start = op.u0; s.env_rel = 0ull; s.env_vel = op.f0; s.env_active = 1; break; /* :383-388 */
+    case SKB_OP_ENV_OFF:      if (s.env_active) s.env_rel = op.u0; break;                   /* :391-395 */
+    case SKB_OP_ENV_RESET:    s.env_start = 0ull; s.env_rel = 0ull; s.env_active = 0; break; /* :377-379 */
+    case SKB_OP_FILTER_CLEAR: s.x1 = s.x2 = s.y1 = s.y2 = 0.0f; break;                      /* :1017-1018 */
+    case SKB_OP_VOICE_CLEAR:  s.sample = 0.0f; s.sm_gain = 0.0f; break;                     /* :1094,1124 */
+    case SKB_OP_SET_PAN:      s.panL = op.f0; s.panR = op.f1; break;                        /* :841-842 */
+    case SKB_OP_SET_SH:       s.sh_count = op.i0; s.sh_hold = op.f0; break;                 /* :1045-1046 */
+    case SKB_OP_SET_PHASE:    s.phase = op.f0; break;
+    default: break;
+  }
+}
+
+
 /* K1  render_free: free_kernel.cuh */
 #include "free_kernel.cuh"
 
@@ -465,24 +484,6 @@ __global__ void k_finish(const float2 *__restrict__ mix, const float *__restrict
 /* ======================================================================== */
 /* K3  state edits at a block boundary                                       */
 /* ======================================================================== */
-/* ops are sorted (stably) by slot on the host; one thread replays one slot's
- * run in order.  op.voice holds the SLOT here. */
-__device__ __forceinline__ void dev_apply_op(VoiceS &s, const skb_op &op) {
-  switch (op.code) {
-    case SKB_OP_TRIGGER:      s.finished = 0; s.phase = op.f0; break;                       /* synth.c:316-339 */
-    case SKB_OP_SET_FINISHED: s.finished = op.i0; break;                                    /* synth.c:281-282 */
-    case SKB_OP_ENV_ON:       s.env_start = op.u0; s.env_rel = 0ull; s.env_vel = op.f0; s.env_active = 1; break; /* :383-388 */
-    case SKB_OP_ENV_OFF:      if (s.env_active) s.env_rel = op.u0; break;                   /* :391-395 */
-    case SKB_OP_ENV_RESET:    s.env_start = 0ull; s.env_rel = 0ull; s.env_active = 0; break; /* :377-379 */
-    case SKB_OP_FILTER_CLEAR: s.x1 = s.x2 = s.y1 = s.y2 = 0.0f; break;                      /* :1017-1018 */
-    case SKB_OP_VOICE_CLEAR:  s.sample = 0.0f; s.sm_gain = 0.0f; break;                     /* :1094,1124 */
-    case SKB_OP_SET_PAN:      s.panL = op.f0; s.panR = op.f1; break;                        /* :841-842 */
-    case SKB_OP_SET_SH:       s.sh_count = op.i0; s.sh_hold = op.f0; break;                 /* :1045-1046 */
-    case SKB_OP_SET_PHASE:    s.phase = op.f0; break;
-    default: break;
-  }
-}
-
 __global__ void k_apply_ops(float4 *__restrict__ sq, int cap, const skb_op *__restrict__ ops,
                             const int2 *__restrict__ runs, int nruns) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

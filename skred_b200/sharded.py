@@ -48,6 +48,9 @@ class ShardedRenderer:
         for b in range(0, frames, lf):
             n = min(lf, frames - b)
             self.api.render_mix(n, ptr + b * 8, self.stream)
+        flush = getattr(self.api.lib, "skb_shim_flush_render", None)
+        if flush is not None:
+            flush()                      # the engine defers and batches its launches
         if self.dist:
             if self.tstream is not None:
                 with self.torch.cuda.stream(self.tstream):

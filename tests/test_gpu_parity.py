@@ -163,3 +163,63 @@ def test_long_launch_equals_callbacks_with_envelopes_and_one_shots(luts):
     ob = b.render(8192 + 300, block=8192 + 300)
     assert maxdiff(oa, ob) <= 1e-7
     assert_state_equal(a.state(), b.state())
+
+
+def _queue(s, timed):
+    import ctypes as C
+    from skred_b200 import workloads as W
+    ev = W.to_skb_events(timed)
+    s.lib.skb_shim_queue_events.argtypes = [C.c_void_p, C.c_int]
+    assert s.lib.skb_shim_queue_events(ev.ctypes.data, len(ev)) == 0
+    return ev
+
+
+@pytest.mark.parametrize("which", ["config4_64_dense", "config5_1024"])
+def test_batched_launch_applies_events_in_kernel(which, luts):
+    """synth(4096) with timestamped events queued: the engine renders the 8 callbacks in ONE launch
+    and applies triggers / envelope on-off at the 512-frame boundaries inside the kernel.  Against
+    the CPU restatement fed the same queue one callback at a time: every evolving word of every
+    voice bit-identical (event timing included), mix within the float budget."""
+    from skred_b200 import workloads as W
+    if which == "config4_64_dense":
+        V, frames = 64, 6 * 4096
+        wl = W.config4(V, seconds=frames / 44100.0, rate_hz=60.0)       # ~45 events per callback on 64 voices
+    else:
+        V, frames = 1024, 6 * 4096
+        wl = W.config5(V, seconds=600.0, luts=luts, event_seconds=frames / 44100.0 + 1.0, stationary=True)
+        # make it busy: every voice is re-triggered several times inside the test
+        wl["timed"] = sorted(wl["timed"] + [(int((0.05 + 0.37 * (v % 7) / 7.0 + 0.11 * k) * 44100),
+                                             ("voice_trigger", v) if v % 3 == 2 else ("envelope_velocity", v, float(k % 2)))
+                                            for v in range(V) for k in range(5)], key=lambda x: x[0])
+    a, b = O.PortSkred(V, run_seq=False), O.DropinCuda(V, run_seq=False)
+    for s in (a, b):
+        W.install(s, wl)
+        _queue(s, wl["timed"])
+    oa = a.render(frames, block=512)
+    st0 = b.engine_stats()
+    ob = b.render(frames, block=4096)
+    st1 = b.engine_stats()
+    assert maxdiff(oa, ob) <= FULL_SCALE_TOL
+    assert_state_equal(a.state(), b.state(), exact_keys=EXACT)
+    # it really was batched: far fewer launches than callbacks (3 kernels per launch: ops, render, reduce)
+    assert st1.kernel_launches - st0.kernel_launches <= 10 * (frames // 4096)      # unbatched: 24 per call
+
+
+def test_batched_equals_unbatched(luts, monkeypatch):
+    """Same engine with batching off (one launch per callback, events by k_apply_ops): identical state."""
+    from skred_b200 import workloads as W
+    V, frames = 1024, 4 * 4096
+    wl = W.config5(V, seconds=600.0, luts=luts, event_seconds=frames / 44100.0 + 1.0, stationary=True)
+    wl["timed"] = sorted(wl["timed"] + [(int((0.03 + 0.29 * (v % 5) / 5.0) * 44100), ("voice_trigger", v) if v % 3 == 2
+                                         else ("envelope_velocity", v, 0.0)) for v in range(V)], key=lambda x: x[0])
+    a = O.DropinCuda(V, run_seq=False)
+    W.install(a, wl)
+    _queue(a, wl["timed"])
+    oa = a.render(frames, block=4096)
+    monkeypatch.setenv("SKB_NO_BATCH", "1")
+    b = O.DropinCuda(V, run_seq=False)
+    W.install(b, wl)
+    _queue(b, wl["timed"])
+    ob = b.render(frames, block=4096)
+    assert maxdiff(oa, ob) <= 1e-6
+    assert_state_equal(a.state(), b.state())
