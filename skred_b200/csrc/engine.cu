@@ -678,6 +678,9 @@ static int batch_launch(skb_engine *e) {
   const int nwin = (int)e->batch.win_frames.size();
   const size_t nops = e->batch.ops.size();
   e->batch.win_ob.push_back((int)nops);                       /* CSR sentinel */
+  for (int w = 0; w < nwin; w++)                              /* per boundary: by slot, queue order within a voice */
+    std::stable_sort(e->batch.ops.begin() + e->batch.win_ob[w], e->batch.ops.begin() + e->batch.win_ob[w + 1],
+                     [](const skb_op &a, const skb_op &b) { return a.voice < b.voice; });
   cudaError_t r;
   if (wait_staging(e)) return e->err;
   const size_t nwi = (size_t)2 * nwin + 1;

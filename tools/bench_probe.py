@@ -15,22 +15,23 @@ from skred_b200.host import load_engine_lib  # noqa: E402
 V = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 EV = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+BLK = int(sys.argv[4]) if len(sys.argv) > 4 else 512          # frames per synth() call
 luts = dict(np.load(os.path.join(ROOT, "tests", "golden", "notamy_luts.npz")))
-sk = Skred(V, max_frames=512)
-wl = W.config5(V, seconds=600.0, luts=luts, event_seconds=(N * 512 / 44100.0 + 1.0) if EV else 0.0, stationary=True)
+sk = Skred(V, max_frames=max(512, BLK))
+wl = W.config5(V, seconds=600.0, luts=luts, event_seconds=(N * BLK / 44100.0 + 1.0) if EV else 0.0, stationary=True)
 W.install(sk, wl)
 if EV:
     ev = W.to_skb_events(wl["timed"])
     sk.lib.skb_shim_queue_events.argtypes = [C.c_void_p, C.c_int]
     sk.lib.skb_shim_queue_events(ev.ctypes.data, len(ev))
-out = np.zeros((512, 2), dtype=np.float32)
+out = np.zeros((BLK, 2), dtype=np.float32)
 prev = sk.stats()
 base = prev
 for k in range(N):
-    sk.lib.synth(out.ctypes.data, None, 512, 2, None)
+    sk.lib.synth(out.ctypes.data, None, BLK, 2, None)
     st = sk.stats()
     cr = [int(a - b) for a, b in zip(st.class_rows, prev.class_rows)]
-    act = (st.active_voice_frames - prev.active_voice_frames) / (V * 512)
+    act = (st.active_voice_frames - prev.active_voice_frames) / (V * BLK)
     if k < 3 or k % 8 == 0 or k == N - 1:
         print("launch %3d  kernel %.3f ms  active %.3f  rows/class [none none+f pw pw+f pow pow+f mixed generic] = %s" %
               (k, st.last_render_ms, act, cr), flush=True)
@@ -52,7 +53,7 @@ eng.skb_debug_slot_rank.argtypes = [C.c_void_p, C.c_int]
 n = eng.skb_debug_cta_phases(sk.engine, ph.ctypes.data, rows.ctypes.data, 160, C.byref(cap))
 us = ph[:n].astype(np.float64) / 1965.0
 tot = us.sum(axis=1)
-names = "compact setup tables prepass render wait rowsum store".split()
+names = "compact setup events+rows prepass render wait rowsum store".split()
 print("per-CTA body us: min %.1f  mean %.1f  max %.1f" % (tot.min(), tot.mean(), tot.max()))
 for k, nm in enumerate(names):
     print("   %-8s min %6.1f mean %6.1f max %6.1f" % (nm, us[:, k].min(), us[:, k].mean(), us[:, k].max()))
