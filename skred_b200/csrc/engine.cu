@@ -260,8 +260,8 @@ int skb_table_upload(skb_engine *e, const float *data, int size) {
   cudaSetDevice(e->cfg.device);
   if (batch_launch(e)) return e->err;
   const size_t need = e->tables_used + (size_t)((size + 31) & ~31);   /* 128-byte aligned starts */
-  if (need > e->tables_cap) {
-    size_t ncap = std::max(need, e->tables_cap * 2);
+  if (need + SKB_TBL_CHUNK > e->tables_cap) {               /* slack: the table cache copies whole chunks */
+    size_t ncap = std::max(need + SKB_TBL_CHUNK, e->tables_cap * 2);
     float *nt = nullptr;
     CK(cudaMalloc((void **)&nt, ncap * sizeof(float)));
     CK(cudaStreamSynchronize(e->last_stream ? e->last_stream : e->stream));
