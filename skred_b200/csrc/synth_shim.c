@@ -282,8 +282,11 @@ void osc_set_freq(int v, float f) {
   touch(v);
 }
 
+static int g_noise_voices = 0;      /* voices on WAVE_TABLE_NOISE_ALT: the only consumers of the per-frame draw */
+
 void osc_set_wave_table_index(int voice, int wave) {
   if (!(wave_table_data[wave] && wave_size[wave] && wave_rate[wave] > 0.0)) return;   /* :278 */
+  g_noise_voices += (wave == WAVE_TABLE_NOISE_ALT) - (voice_wave_table_index[voice] == WAVE_TABLE_NOISE_ALT);
   voice_wave_table_index[voice] = wave;
   voice_finished[voice] = wave_one_shot[wave] ? 1 : 0;                                   /* :281-282 */
   push_op(voice, SKB_OP_SET_FINISHED, voice_finished[voice], 0, 0, 0);
@@ -607,6 +610,7 @@ int voice_copy(int v, int n) {
 void voice_reset(int i) {
   /* synth.c:1090-1132.  Deliberately NOT reset (App. B `S`): phase, S&H
    * state, cz_*, amp/pan mod depth, envelope velocity. */
+  g_noise_voices -= (voice_wave_table_index[i] == WAVE_TABLE_NOISE_ALT);
   voice_wave_table_index[i] = 0;
   voice_table_rate[i] = 0;
   voice_table_size[i] = 0;
@@ -660,8 +664,7 @@ int envelope_velocity(int voice, float f) {
   if (f == 0) {
     amp_envelope_release(voice);
   } else {
-    voice_use_amp_envelope[voice] = 1;
-    touch(voice);
+    if (!voice_use_amp_envelope[voice]) { voice_use_amp_envelope[voice] = 1; touch(voice); }   /* (a re-trigger changes no parameter) */
     if (voice_one_shot[voice]) osc_trigger(voice);
     amp_envelope_trigger(voice, f);
   }
@@ -945,7 +948,19 @@ static int step_traces(int n, int append) {
   const int base = append ? g_gain_fill : 0;
   ensure_traces(base + n);
   if (!g_rng_seeded) { audio_rng_init(&g_rng, 1); g_rng_seeded = 1; }      /* synth.c:508 */
-  for (int i = 0; i < n; i++) g_noise[i] = audio_rng_float(&g_rng);
+  if (g_noise_voices > 0) {
+    for (int i = 0; i < n; i++) g_noise[i] = audio_rng_float(&g_rng);
+  } else {
+    /* nobody listens: the reference still draws once per frame (synth.c:525), so the generator
+     * must end up n steps further — x -> a^n x + c (a^n - 1)/(a - 1) (mod 2^64) by squaring */
+    uint64_t am = 6364136223846793005ULL, cm = 1442695040888963407ULL, an = 1, cn = 0;
+    for (unsigned k = (unsigned)n; k; k >>= 1) {
+      if (k & 1) { an *= am; cn = cn * am + cm; }
+      cm = (am + 1) * cm;
+      am *= am;
+    }
+    g_rng = an * g_rng + cn;
+  }
   float g = volume_smoother_gain;
   const float k = volume_smoother_smoothing, target = volume_final;
   for (int i = 0; i < n; i++) { g += k * (target - g); g_gain[base + i] = g; }

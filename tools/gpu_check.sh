@@ -20,6 +20,6 @@ if [[ "$WHAT" == *ncu* ]]; then
   timeout 600 python bench.py $NARGS > gpurun_out/plain.log 2>&1 &&
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py $NARGS > gpurun_out/ncu1.log 2>&1
   timeout 600 python bench.py $NARGS > gpurun_out/plain2.log 2>&1 &&
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_render_free -s 30 -c 2 -o gpurun_out/prof -f python bench.py $NARGS > gpurun_out/ncu2.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_render_free -s 6 -c 1 -o gpurun_out/prof -f python bench.py $NARGS > gpurun_out/ncu2.log 2>&1
   tail -3 gpurun_out/ncu2.log
 fi
