@@ -154,6 +154,11 @@ typedef struct skb_config {
 #define SKB_CFG_FORCE_GENERIC 1u
 /* testing aid: one launch per skb_render_mix call (no batching of consecutive callbacks) */
 #define SKB_CFG_NO_BATCH 2u
+/* opt-in: render launches of >= 4 windows TIME-SPLIT (free_kernel.cuh: pass A advances every voice through
+ * the launch with the light recurrences and snapshots its state per window, pass B renders the windows in
+ * parallel, pass C runs the biquads).  Bit-identical state, same mix within the regrouping of the sum; measured
+ * on B200 it does not pay (profiles/r01_time_split.txt), so the default is the sequential kernel. */
+#define SKB_CFG_WIDE 4u
 
 int  skb_create(skb_engine **out, const skb_config *cfg);
 void skb_destroy(skb_engine *e);
@@ -243,6 +248,10 @@ typedef struct skb_stats {
                                  (compaction, voice set-up, table cache, envelope pre-pass, render, wait for the
                                  slowest warp, row sum, final store), summed over CTAs and launches */
   uint64_t cta_batches;       /* ... and how many (CTA, batch) passes that covers */
+  uint64_t wide_launches;     /* launches rendered time-split (pass A advance, pass B windows, pass C biquad) */
+  uint64_t wide_errors;       /* rows a time-split pass had to drop (must stay 0) */
+  float    last_wide_ms[3];   /* device time of passes A, B, C (+ row reduce) of the last time-split launch */
+  int32_t  _pad2;
 } skb_stats;
 int  skb_get_stats(skb_engine *e, skb_stats *out);
 
@@ -250,6 +259,7 @@ int  skb_get_stats(skb_engine *e, skb_stats *out);
  * free-voice kernel and the planner's row lists; class rank of the voice in a slot. */
 int  skb_debug_cta_phases(skb_engine *e, uint64_t *phases, int32_t *rows, int max_ctas, int *rows_cap);
 int  skb_debug_slot_rank(skb_engine *e, int slot);
+int  skb_debug_warp_clocks(skb_engine *e, uint64_t *out, int max_ctas);
 
 /* "cuda-sm100a" for the product, "cpu-port" for the oracle build. */
 const char *skb_backend_name(void);

@@ -415,6 +415,7 @@ int skb_debug_cta_phases(skb_engine *e, uint64_t *phases, int32_t *rows, int max
   return 0;
 }
 int skb_debug_slot_rank(skb_engine *e, int slot) { (void)e; (void)slot; return -1; }
+int skb_debug_warp_clocks(skb_engine *e, uint64_t *out, int max_ctas) { (void)e; (void)out; (void)max_ctas; return 0; }
 
 int skb_snapshot(skb_engine *e, int first, int n, skb_voice_state *out) {
   if (!e || first < 0 || n < 0 || first + n > e->n || !out) return fail(e, SKB_ERR_ARG, "snapshot: bad range");

@@ -43,7 +43,7 @@ struct skb_engine {
   char errtxt[512] = {0};
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_h2d = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
-  bool timing_pending = false;
+  bool timing_pending = false, wide_timing_pending = false;
 
   /* host mirror of what the host sent */
   std::vector<skb_voice_params> par;
@@ -67,6 +67,17 @@ struct skb_engine {
   unsigned long long *d_ctaphase = nullptr; size_t ctaphase_cap = 0;   /* diagnostics: per-CTA phase clocks of the last launch */
   int n_sm = 148, free_ctas = 0, free_groups = 0, n_prows = 0;   /* partial rows: one per (CTA, batch) of k_render_free, one per bin */
 
+  /* time-split ("wide") launches: free_kernel.cuh, passes A / B / C */
+  struct RowList { int off = 0, ctas = 0, rows_cap = 0; };   /* rows at d_lists + off: [ctas][rows_cap] */
+  RowList list_a_wide, list_c;
+  std::vector<RowList> list_b;       /* indexed by the number of windows of the launch */
+  int *d_lists = nullptr; size_t lists_cap = 0;
+  int n_wide_rows = 0, n_xrows = 0, snap_nwin = 0;
+  int *d_xrow = nullptr; size_t xrow_cap = 0;
+  float4 *d_snap = nullptr; size_t snap_cap = 0;
+  float *d_xs = nullptr; size_t xs_cap = 0;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+
   /* device */
   float4 *d_pq = nullptr, *d_sq[2] = {nullptr, nullptr};
   int cur = 0;
@@ -85,7 +96,7 @@ struct skb_engine {
   float4 *d_recs = nullptr; size_t d_recs_cap = 0;
   skb_op *d_ops = nullptr; size_t d_ops_cap = 0;
   int2 *d_runs = nullptr; size_t d_runs_cap = 0;
-  skb_voice_state *d_snap = nullptr; size_t d_snap_cap = 0;
+  skb_voice_state *d_vsnap = nullptr; size_t d_vsnap_cap = 0;
 
   /* pinned staging */
   float *h_gain = nullptr, *h_noise = nullptr, *h_out = nullptr;
@@ -207,7 +218,12 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
             cudaMallocHost((void **)&e->h_counters, SKB_N_COUNTERS * sizeof(unsigned long long)) == cudaSuccess &&
             cudaMemset(e->d_tickets, 0, (size_t)(mf / SKB_RED_X + 1) * sizeof(unsigned int)) == cudaSuccess &&
             cudaMemset(e->d_counters, 0, SKB_N_COUNTERS * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaEventCreate(&e->ev_a) == cudaSuccess && cudaEventCreate(&e->ev_b) == cudaSuccess &&
             cudaFuncSetAttribute(k_render_free, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)skb_free_smem_bytes()) == cudaSuccess &&
+            cudaFuncSetAttribute(k_render_window, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)skb_free_smem_bytes()) == cudaSuccess &&
+            cudaFuncSetAttribute(k_render_biquad, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)skb_free_smem_bytes()) == cudaSuccess &&
             cudaMallocHost((void **)&e->h_gain, (size_t)mf * sizeof(float)) == cudaSuccess &&
             cudaMallocHost((void **)&e->h_noise, (size_t)mf * sizeof(float)) == cudaSuccess &&
@@ -237,9 +253,12 @@ void skb_destroy(skb_engine *e) {
   cudaFree(e->d_pq); cudaFree(e->d_sq[0]); cudaFree(e->d_sq[1]); cudaFree(e->d_tables);
   cudaFree(e->d_bins); cudaFree(e->d_partials); cudaFree(e->d_mix); cudaFree(e->d_out);
   cudaFree(e->d_gain); cudaFree(e->d_noise); cudaFree(e->d_idx); cudaFree(e->d_recs);
-  cudaFree(e->d_ops); cudaFree(e->d_runs); cudaFree(e->d_snap);
+  cudaFree(e->d_ops); cudaFree(e->d_runs); cudaFree(e->d_vsnap);
   cudaFree(e->d_envbuf); cudaFree(e->d_ctarows); cudaFree(e->d_ctaphase);
   cudaFree(e->d_win); cudaFree(e->d_bops); cudaFree(e->d_wake);
+  cudaFree(e->d_lists); cudaFree(e->d_xrow); cudaFree(e->d_snap); cudaFree(e->d_xs);
+  if (e->ev_a) cudaEventDestroy(e->ev_a);
+  if (e->ev_b) cudaEventDestroy(e->ev_b);
   cudaFreeHost(e->h_win); cudaFreeHost(e->h_bops); cudaFreeHost(e->h_wake);
   cudaFree(e->d_part2); cudaFree(e->d_tickets); cudaFree(e->d_counters);
   cudaFreeHost(e->h_counters);
@@ -443,44 +462,121 @@ static int replan(skb_engine *e, cudaStream_t st) {
   e->n_free_rows = e->n_free_pad / 32;
   /* partial-row groups: one per (CTA, batch) of k_render_free, then the bins 16 to a group */
   std::vector<int> ctarows;
+  std::vector<int> lists;                    /* row lists of the time-split passes, uploaded as one array */
   {
     /* Rows -> CTAs, balanced by estimated cost (LPT: costliest row first, to the least loaded
      * CTA).  One CTA per SM; a CTA renders its rows in batches of SKB_CTA_WARPS, all rows of a
      * batch concurrently, so its time is roughly (sum of row costs) / issue rate. */
     static const int cost_of_rank[8] = {0, 20, 24, 29, 36, 36, 46, 160};   /* instructions per voice-frame, measured */
     const int nrows = e->n_free_rows;
-    e->free_ctas = std::min(e->n_sm, nrows);
-    const int nb = e->free_ctas ? ((nrows + e->free_ctas - 1) / e->free_ctas + SKB_CTA_WARPS - 1) / SKB_CTA_WARPS : 0;
-    e->rows_cap = nb * SKB_CTA_WARPS;
-    e->free_groups = e->free_ctas * nb;
-    std::vector<std::pair<int, int>> rc((size_t)nrows);                    /* (cost, row) */
+    std::vector<int> row_rank((size_t)nrows, 0), row_cost((size_t)nrows, 0);
+    std::vector<uint8_t> row_wide((size_t)nrows, 0), row_filt((size_t)nrows, 0);
+    e->n_wide_rows = 0;
+    std::vector<int> xrow((size_t)std::max(nrows, 1), -1);
+    e->n_xrows = 0;
     for (int r = 0; r < nrows; r++) {
-      int cost = 0;
-      for (int l = 0; l < 32 && !cost; l++) {
+      int cost = 0, rank = 0;
+      bool oneshot_any = false, any = false;
+      for (int l = 0; l < 32; l++) {
         const int v = e->voice_of_slot[r * 32 + l];
         if (v < 0) continue;
-        const uint64_t key = feature_key(&e->par[v]);
-        cost = cost_of_rank[(key >> SKB_KEY_CLASS_SHIFT) & 7];
-        if (e->par[v].flags & SKB_F_ONE_SHOT) cost = (cost + 3) / 4;      /* one-shots are mostly over; the kernel packs the rest */
+        any = true;
+        if (e->par[v].flags & SKB_F_ONE_SHOT) oneshot_any = true;
+        if (!cost) {
+          const uint64_t key = feature_key(&e->par[v]);
+          rank = (int)((key >> SKB_KEY_CLASS_SHIFT) & 7);
+          cost = cost_of_rank[rank];
+          if (e->par[v].flags & SKB_F_ONE_SHOT) cost = (cost + 3) / 4;      /* one-shots are mostly over; the kernel packs the rest */
+        }
       }
-      rc[r] = std::make_pair(cost, r);
+      row_rank[r] = rank; row_cost[r] = cost;
+      /* time-split eligibility: a pipelined class (rows are class-pure), and a row with a filter holds no
+       * one-shot voice (pass C carries the biquad across windows without the one-shot end logic) */
+      const bool filt = rank == 3 || rank == 4 || rank == 6;
+      row_filt[r] = filt ? 1 : 0;
+      if (any && rank >= 1 && rank <= 6 && !(filt && oneshot_any) && (e->cfg.flags & SKB_CFG_WIDE) && !(e->cfg.flags & SKB_CFG_FORCE_GENERIC)) {
+        row_wide[r] = 1;
+        e->n_wide_rows++;
+        if (filt) xrow[r] = e->n_xrows++;
+      }
     }
-    std::vector<std::pair<int, int>> order = rc;
-    std::stable_sort(order.begin(), order.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.first > b.first; });
-    typedef std::pair<long long, int> Load;                                /* (load, cta) */
-    std::priority_queue<Load, std::vector<Load>, std::greater<Load>> pqd;
-    for (int c = 0; c < e->free_ctas; c++) pqd.push(Load(0, c));
-    std::vector<std::vector<std::pair<int, int>>> mine((size_t)e->free_ctas);
-    for (size_t i = 0; i < order.size(); i++) {
-      Load l = pqd.top(); pqd.pop();
-      mine[l.second].push_back(order[i]);
-      l.first += order[i].first;
-      if ((int)mine[l.second].size() < e->rows_cap) pqd.push(l);          /* a full CTA leaves the heap */
+    /* deal `items` = (cost, row entry) to at most max_ctas CTAs; returns [ctas][rows_cap], -1 padded */
+    auto deal = [](std::vector<std::pair<int, int>> items, int max_ctas, std::vector<int> &out, int *ctas_out, int *cap_out) {
+      const int n = (int)items.size();
+      const int ctas = std::max(1, std::min(max_ctas, n));
+      const int nb = n ? ((n + ctas - 1) / ctas + SKB_CTA_WARPS - 1) / SKB_CTA_WARPS : 0;
+      const int rcap = nb * SKB_CTA_WARPS;
+      std::stable_sort(items.begin(), items.end(), [](const std::pair<int, int> &x, const std::pair<int, int> &y) { return x.first > y.first; });
+      typedef std::pair<long long, int> Load;                                /* (load, cta) */
+      std::priority_queue<Load, std::vector<Load>, std::greater<Load>> pqd;
+      for (int c = 0; c < ctas; c++) pqd.push(Load(0, c));
+      std::vector<std::vector<std::pair<int, int>>> mine((size_t)ctas);
+      for (size_t i = 0; i < items.size(); i++) {
+        Load l = pqd.top(); pqd.pop();
+        mine[l.second].push_back(items[i]);
+        l.first += items[i].first;
+        if ((int)mine[l.second].size() < rcap) pqd.push(l);                /* a full CTA leaves the heap */
+      }
+      out.assign((size_t)std::max(ctas * rcap, 1), -1);
+      for (int c = 0; c < ctas; c++) {
+        std::stable_sort(mine[c].begin(), mine[c].end(), [](const std::pair<int, int> &x, const std::pair<int, int> &y) {
+          return x.first != y.first ? x.first < y.first : (x.second & ~SKB_ROW_WIDE) < (y.second & ~SKB_ROW_WIDE); });   /* cheapest first: costliest = highest warp id */
+        for (size_t k = 0; k < mine[c].size(); k++) out[(size_t)c * rcap + k] = mine[c][k].second;
+      }
+      *ctas_out = n ? ctas : 0; *cap_out = rcap;
+    };
+    std::vector<std::pair<int, int>> items((size_t)nrows);
+    for (int r = 0; r < nrows; r++) items[r] = std::make_pair(row_cost[r], r);
+    deal(items, e->n_sm, ctarows, &e->free_ctas, &e->rows_cap);
+    e->free_groups = e->free_ctas * (e->rows_cap / SKB_CTA_WARPS);
+    /* pass A of a time-split launch: the same rows, the wide ones flagged and costed as the light body */
+    auto append = [&lists](const std::vector<int> &l, int ctas, int rcap) {
+      skb_engine::RowList rl; rl.off = (int)lists.size(); rl.ctas = ctas; rl.rows_cap = rcap;
+      lists.insert(lists.end(), l.begin(), l.end());
+      return rl;
+    };
+    e->list_b.clear();
+    e->list_a_wide = skb_engine::RowList(); e->list_c = skb_engine::RowList();
+    if (e->n_wide_rows > 0) {
+      std::vector<int> l; int ctas = 0, rcap = 0;
+      for (int r = 0; r < nrows; r++) items[r] = row_wide[r] ? std::make_pair(5, r | SKB_ROW_WIDE) : std::make_pair(row_cost[r], r);
+      deal(items, e->n_sm, l, &ctas, &rcap);
+      if (ctas != e->free_ctas || rcap != e->rows_cap) return fail(e, SKB_ERR_STATE, "planner: pass A list shape");
+      e->list_a_wide = append(l, ctas, rcap);
+      /* pass C: rows with a filter, the biquad / gain / mix part */
+      items.clear();
+      for (int r = 0; r < nrows; r++) if (row_wide[r] && row_filt[r]) items.push_back(std::make_pair(16, r));
+      if (!items.empty()) { deal(items, e->n_sm, l, &ctas, &rcap); e->list_c = append(l, ctas, rcap); }
+      /* pass B, per number of windows W of a launch: floor(#SM / W) CTAs per window */
+      items.clear();
+      for (int r = 0; r < nrows; r++)
+        if (row_wide[r]) items.push_back(std::make_pair(row_filt[r] ? std::max(row_cost[r] - 14, 4) : row_cost[r], r));
+      const int wmax = (e->cfg.max_frames + SKB_ENV_WIN - 1) / SKB_ENV_WIN;
+      e->list_b.assign((size_t)wmax + 1, skb_engine::RowList());
+      for (int W = SKB_WIDE_MIN_WIN; W <= wmax && W <= e->n_sm; W++) {
+        deal(items, std::max(1, e->n_sm / W), l, &ctas, &rcap);
+        e->list_b[W] = append(l, ctas, rcap);
+      }
+      e->snap_nwin = wmax;
     }
-    ctarows.assign((size_t)std::max(e->free_ctas * e->rows_cap, 1), -1);
-    for (int c = 0; c < e->free_ctas; c++) {
-      std::sort(mine[c].begin(), mine[c].end());                          /* cheapest first: costliest = highest warp id */
-      for (size_t k = 0; k < mine[c].size(); k++) ctarows[(size_t)c * e->rows_cap + k] = mine[c][k].second;
+    {
+      cudaError_t rr = grow_dev(&e->d_xrow, &e->xrow_cap, xrow.size());
+      if (rr != cudaSuccess) return fail(e, SKB_ERR_CUDA, "x row map alloc", cudaGetErrorString(rr));
+      CK(cudaMemcpyAsync(e->d_xrow, xrow.data(), xrow.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+      if (!lists.empty()) {
+        rr = grow_dev(&e->d_lists, &e->lists_cap, lists.size());
+        if (rr != cudaSuccess) return fail(e, SKB_ERR_CUDA, "row list alloc", cudaGetErrorString(rr));
+        CK(cudaMemcpyAsync(e->d_lists, lists.data(), lists.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+      }
+      CK(cudaStreamSynchronize(st));          /* pageable sources */
+      if (e->n_wide_rows > 0) {
+        rr = grow_dev(&e->d_snap, &e->snap_cap, (size_t)SKB_NSQ * e->snap_nwin * e->cap);
+        if (rr != cudaSuccess) return fail(e, SKB_ERR_CUDA, "window snapshot alloc", cudaGetErrorString(rr));
+      }
+      if (e->n_xrows > 0) {
+        rr = grow_dev(&e->d_xs, &e->xs_cap, (size_t)e->n_xrows * e->cfg.max_frames * 32);
+        if (rr != cudaSuccess) return fail(e, SKB_ERR_CUDA, "x scratch alloc", cudaGetErrorString(rr));
+      }
     }
   }
   e->n_prows = e->free_groups + (int)binv.size();
@@ -545,9 +641,9 @@ static int replan(skb_engine *e, cudaStream_t st) {
     CK(cudaMemcpyAsync(e->d_ctarows, ctarows.data(), ctarows.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
     e->h_ctarows = ctarows;
-    rr = grow_dev(&e->d_ctaphase, &e->ctaphase_cap, (size_t)std::max(e->free_ctas, 1) * 8);
+    rr = grow_dev(&e->d_ctaphase, &e->ctaphase_cap, (size_t)std::max(e->n_sm, 1) * (8 + SKB_CTA_WARPS));
     if (rr != cudaSuccess) return fail(e, SKB_ERR_CUDA, "phase clock alloc", cudaGetErrorString(rr));
-    rr = grow_dev(&e->d_envbuf, &e->envbuf_cap, (size_t)std::max(e->free_ctas, 1) * SKB_CTA_THREADS * SKB_ENV_WIN);
+    rr = grow_dev(&e->d_envbuf, &e->envbuf_cap, (size_t)std::max(e->n_sm, 1) * SKB_CTA_THREADS * SKB_ENV_WIN);   /* per CTA of any pass */
     if (rr != cudaSuccess) return fail(e, SKB_ERR_CUDA, "envelope scratch alloc", cudaGetErrorString(rr));
   }
   /* every owned voice gets a fresh record */
@@ -706,7 +802,14 @@ static int batch_launch(skb_engine *e) {
   if (e->any_noise)
     CK(cudaMemcpyAsync(e->d_noise, e->h_noise, (size_t)nframes * sizeof(float), cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(e->ev_h2d, st));
-  const size_t n_prow = (size_t)std::max(e->n_prows, 1);
+  /* time-split launch?  Needs enough windows to split, eligible rows, and no modulation bins */
+  const bool wide = e->n_wide_rows > 0 && nwin >= SKB_WIDE_MIN_WIN && nwin < (int)e->list_b.size() &&
+                    e->list_b[nwin].ctas > 0 && e->bins.empty() && (e->cfg.flags & SKB_CFG_WIDE);
+  const skb_engine::RowList lb = wide ? e->list_b[nwin] : skb_engine::RowList();
+  const int groups_b = wide ? lb.ctas * (lb.rows_cap / SKB_CTA_WARPS) : 0;
+  const int groups_c = (wide && e->list_c.ctas > 0) ? e->list_c.ctas * (e->list_c.rows_cap / SKB_CTA_WARPS) : 0;
+  const int n_prows_now = wide ? e->free_groups + groups_b + groups_c : e->n_prows;
+  const size_t n_prow = (size_t)std::max(n_prows_now, 1);
   if (n_prow * (size_t)e->cfg.max_frames > e->partials_cap) {
     CK(cudaStreamSynchronize(st));
     r = grow_dev(&e->d_partials, &e->partials_cap, n_prow * (size_t)e->cfg.max_frames);
@@ -714,13 +817,45 @@ static int batch_launch(skb_engine *e) {
   }
   CK(cudaEventRecord(e->ev_t0, st));
   if (e->n_free_rows > 0) {
-    k_render_free<<<e->free_ctas, SKB_CTA_THREADS, skb_free_smem_bytes(), st>>>(
-        e->d_pq, e->d_sq[e->cur], e->cap, e->n_free_rows, e->n_free_pad, e->d_ctarows, e->rows_cap,
-        e->d_tables, e->d_noise, nframes, (unsigned long long)e->batch.ssc0,
-        e->d_win, e->d_win + nwin, nwin, e->d_bops, d_wake,
-        e->d_partials, nframes, e->d_envbuf, e->d_counters, e->d_ctaphase,
-        (e->cfg.flags & SKB_CFG_FORCE_GENERIC) ? 1 : 0);
+    FreeArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.pq = e->d_pq; fa.sq = e->d_sq[e->cur]; fa.cap = e->cap; fa.n_rows = e->n_free_rows; fa.n_free = e->n_free_pad;
+    fa.cta_rowlist = wide ? e->d_lists + e->list_a_wide.off : e->d_ctarows; fa.rows_cap = e->rows_cap;
+    fa.tables = e->d_tables; fa.noise = e->d_noise;
+    fa.nframes = nframes; fa.ssc_before = (unsigned long long)e->batch.ssc0;
+    fa.win_frames = e->d_win; fa.win_ob = e->d_win + nwin; fa.nwin = nwin;
+    fa.bops = e->d_bops; fa.wake = d_wake;
+    fa.ctarows = e->d_partials; fa.row_stride = nframes;
+    fa.envbuf = e->d_envbuf; fa.counters = e->d_counters; fa.cta_phase = e->d_ctaphase;
+    fa.force_generic = (e->cfg.flags & SKB_CFG_FORCE_GENERIC) ? 1 : 0;
+    fa.wide_on = wide ? 1 : 0;
+    fa.snap = e->d_snap; fa.snap_nwin = e->snap_nwin;
+    fa.xs = e->d_xs; fa.xs_frames = e->cfg.max_frames; fa.xrow_of = e->d_xrow;
+    fa.cpw = 0; fa.group0 = 0;
+    { const char *pp = getenv("SKB_PHASE_PASS"); fa.phase_pass = pp ? atoi(pp) : 0; }
+    fa.warp_diag = e->d_ctaphase ? e->d_ctaphase + (size_t)e->n_sm * 8 : nullptr;
+    if (wide)       /* "no snapshot" = finished: group 0 of every window's snapshot */
+      CK(cudaMemsetAsync(e->d_snap, 0x01, (size_t)nwin * e->cap * sizeof(float4), st));
+    k_render_free<<<e->free_ctas, SKB_CTA_THREADS, skb_free_smem_bytes(), st>>>(fa);
     e->stats.kernel_launches++;
+    if (wide) {
+      CK(cudaEventRecord(e->ev_a, st));
+      FreeArgs fb = fa;
+      fb.wide_on = 0; fb.bops = nullptr; fb.wake = nullptr;
+      fb.cta_rowlist = e->d_lists + lb.off; fb.rows_cap = lb.rows_cap; fb.cpw = lb.ctas; fb.group0 = e->free_groups;
+      k_render_window<<<lb.ctas * nwin, SKB_CTA_THREADS, skb_free_smem_bytes(), st>>>(fb);
+      e->stats.kernel_launches++;
+      CK(cudaEventRecord(e->ev_b, st));
+      if (groups_c > 0) {
+        FreeArgs fc = fb;
+        fc.cta_rowlist = e->d_lists + e->list_c.off; fc.rows_cap = e->list_c.rows_cap; fc.cpw = 0;
+        fc.group0 = e->free_groups + groups_b;
+        k_render_biquad<<<e->list_c.ctas, SKB_CTA_THREADS, skb_free_smem_bytes(), st>>>(fc);
+        e->stats.kernel_launches++;
+      }
+      e->stats.wide_launches++;
+      e->wide_timing_pending = true;
+    }
   }
   if (!e->bins.empty()) {                                     /* (a batch with bins is always one segment without in-kernel ops) */
     const int nt = e->max_bin_threads;
@@ -730,10 +865,10 @@ static int batch_launch(skb_engine *e) {
                                                          e->d_partials, nframes, e->d_counters + 1);
     e->stats.kernel_launches++;
   }
-  if (e->n_prows > 0) {
+  if (n_prows_now > 0) {
     dim3 blk(SKB_RED_X, SKB_RED_Y);
-    dim3 grd((nframes + SKB_RED_X - 1) / SKB_RED_X, std::max(1, std::min(SKB_RED_CHUNKS, e->n_prows / 16)));
-    k_reduce_rows<<<grd, blk, 0, st>>>(e->d_partials, e->n_prows, nframes, nframes, e->d_part2,
+    dim3 grd((nframes + SKB_RED_X - 1) / SKB_RED_X, std::max(1, std::min(SKB_RED_CHUNKS, n_prows_now / 16)));
+    k_reduce_rows<<<grd, blk, 0, st>>>(e->d_partials, n_prows_now, nframes, nframes, e->d_part2,
                                        e->d_tickets, (float2 *)e->batch.mix);
     e->stats.kernel_launches++;
   } else {
@@ -834,6 +969,7 @@ int skb_finish(skb_engine *e, const float *d_mix, int nframes, const float *gain
   for (int i = 0; i < 8; i++) e->stats.class_rows[i] = e->h_counters[2 + i];
   for (int i = 0; i < 8; i++) e->stats.phase_cycles[i] = e->h_counters[10 + i];
   e->stats.cta_batches = e->h_counters[18];
+  e->stats.wide_errors = e->h_counters[19];
   if (num_channels == 2) {
     memcpy(out, e->h_out, (size_t)nframes * sizeof(float2));
   } else {
@@ -847,6 +983,13 @@ int skb_finish(skb_engine *e, const float *d_mix, int nframes, const float *gain
     float ms = 0.0f;
     if (cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1) == cudaSuccess) e->stats.last_render_ms = ms;
     else cudaGetLastError();
+    e->stats.last_wide_ms[0] = e->stats.last_wide_ms[1] = e->stats.last_wide_ms[2] = 0.0f;
+    if (e->wide_timing_pending) {
+      if (cudaEventElapsedTime(&ms, e->ev_t0, e->ev_a) == cudaSuccess) e->stats.last_wide_ms[0] = ms; else cudaGetLastError();
+      if (cudaEventElapsedTime(&ms, e->ev_a, e->ev_b) == cudaSuccess) e->stats.last_wide_ms[1] = ms; else cudaGetLastError();
+      if (cudaEventElapsedTime(&ms, e->ev_b, e->ev_t1) == cudaSuccess) e->stats.last_wide_ms[2] = ms; else cudaGetLastError();
+      e->wide_timing_pending = false;
+    }
     e->timing_pending = false;
   }
   return e->err;
@@ -881,10 +1024,18 @@ int skb_sync(skb_engine *e, void *stream) {
   for (int i = 0; i < 8; i++) e->stats.class_rows[i] = e->h_counters[2 + i];
   for (int i = 0; i < 8; i++) e->stats.phase_cycles[i] = e->h_counters[10 + i];
   e->stats.cta_batches = e->h_counters[18];
+  e->stats.wide_errors = e->h_counters[19];
   if (e->timing_pending) {
     float ms = 0.0f;
     if (cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1) == cudaSuccess) e->stats.last_render_ms = ms;
     else cudaGetLastError();
+    e->stats.last_wide_ms[0] = e->stats.last_wide_ms[1] = e->stats.last_wide_ms[2] = 0.0f;
+    if (e->wide_timing_pending) {
+      if (cudaEventElapsedTime(&ms, e->ev_t0, e->ev_a) == cudaSuccess) e->stats.last_wide_ms[0] = ms; else cudaGetLastError();
+      if (cudaEventElapsedTime(&ms, e->ev_a, e->ev_b) == cudaSuccess) e->stats.last_wide_ms[1] = ms; else cudaGetLastError();
+      if (cudaEventElapsedTime(&ms, e->ev_b, e->ev_t1) == cudaSuccess) e->stats.last_wide_ms[2] = ms; else cudaGetLastError();
+      e->wide_timing_pending = false;
+    }
     e->timing_pending = false;
   }
   return e->err;
@@ -896,7 +1047,7 @@ static int stage_slots(skb_engine *e, int first, int n) {
   if ((r = grow_pin(&e->h_idx, &e->h_idx_cap, (size_t)n)) != cudaSuccess ||
       (r = grow_dev(&e->d_idx, &e->d_idx_cap, (size_t)n)) != cudaSuccess ||
       (r = grow_pin(&e->h_snap, &e->h_snap_cap, (size_t)n)) != cudaSuccess ||
-      (r = grow_dev(&e->d_snap, &e->d_snap_cap, (size_t)n)) != cudaSuccess)
+      (r = grow_dev(&e->d_vsnap, &e->d_vsnap_cap, (size_t)n)) != cudaSuccess)
     return fail(e, SKB_ERR_CUDA, "snapshot alloc", cudaGetErrorString(r));
   for (int i = 0; i < n; i++) e->h_idx[i] = e->slot_of_voice[first + i];
   return SKB_OK;
@@ -912,9 +1063,9 @@ int skb_snapshot(skb_engine *e, int first, int n, skb_voice_state *out) {
   if (sync_inputs(e, st)) return e->err;
   if (stage_slots(e, first, n)) return e->err;
   CK(cudaMemcpyAsync(e->d_idx, e->h_idx, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
-  k_gather_state<<<(n + 127) / 128, 128, 0, st>>>(e->d_sq[e->cur], e->cap, e->d_idx, n, e->d_snap);
+  k_gather_state<<<(n + 127) / 128, 128, 0, st>>>(e->d_sq[e->cur], e->cap, e->d_idx, n, e->d_vsnap);
   e->stats.kernel_launches++;
-  CK(cudaMemcpyAsync(e->h_snap, e->d_snap, (size_t)n * sizeof(skb_voice_state), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(e->h_snap, e->d_vsnap, (size_t)n * sizeof(skb_voice_state), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   memcpy(out, e->h_snap, (size_t)n * sizeof(skb_voice_state));
   return e->err;
@@ -931,8 +1082,8 @@ int skb_restore(skb_engine *e, int first, int n, const skb_voice_state *in) {
   if (stage_slots(e, first, n)) return e->err;
   memcpy(e->h_snap, in, (size_t)n * sizeof(skb_voice_state));
   CK(cudaMemcpyAsync(e->d_idx, e->h_idx, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(e->d_snap, e->h_snap, (size_t)n * sizeof(skb_voice_state), cudaMemcpyHostToDevice, st));
-  k_scatter_state<<<(n + 127) / 128, 128, 0, st>>>(e->d_sq[e->cur], e->cap, e->d_idx, n, e->d_snap);
+  CK(cudaMemcpyAsync(e->d_vsnap, e->h_snap, (size_t)n * sizeof(skb_voice_state), cudaMemcpyHostToDevice, st));
+  k_scatter_state<<<(n + 127) / 128, 128, 0, st>>>(e->d_sq[e->cur], e->cap, e->d_idx, n, e->d_vsnap);
   e->stats.kernel_launches++;
   CK(cudaStreamSynchronize(st));
   return e->err;
@@ -951,6 +1102,19 @@ int skb_debug_cta_phases(skb_engine *e, uint64_t *phases, int32_t *rows, int max
   CK(cudaMemcpy(phases, e->d_ctaphase, (size_t)n * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   if (rows_cap) *rows_cap = e->rows_cap;
   if (rows) memcpy(rows, e->h_ctarows.data(), (size_t)n * e->rows_cap * sizeof(int32_t));
+  return n;
+}
+
+/* Diagnostics: per physical warp of the first batch of every CTA of the last launch: render cycles (bits 0-46),
+ * dyn body (bit 47), live lanes (48-55), class (56-63).  Returns the number of CTAs written. */
+int skb_debug_warp_clocks(skb_engine *e, uint64_t *out, int max_ctas) {
+  if (!e || !out || max_ctas <= 0) return SKB_ERR_ARG;
+  cudaSetDevice(e->cfg.device);
+  const int n = std::min(max_ctas, e->n_sm);
+  if (n <= 0 || !e->d_ctaphase) return 0;
+  if (batch_launch(e)) return e->err;
+  CK(cudaStreamSynchronize(e->last_stream ? e->last_stream : e->stream));
+  CK(cudaMemcpy(out, e->d_ctaphase + (size_t)e->n_sm * 8, (size_t)n * SKB_CTA_WARPS * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   return n;
 }
 

@@ -48,6 +48,8 @@ struct VoiceS {
   float y2; int env_active; float env_vel, sm_gain;
   float panL, panR; unsigned long long env_start;
   unsigned long long env_rel;
+  int aux;                   /* spare word of the record: 0 in the state proper; in a window snapshot of a time-split
+                                launch bit 0 = "mmf_init ran at this boundary" (free_kernel.cuh) */
   int nact;                  /* frames actually rendered (not skipped) in this launch; not stored */
 };
 
@@ -76,6 +78,7 @@ __device__ __forceinline__ void load_state(const float4 *__restrict__ q, int cap
   s.env_start = ((unsigned long long)__float_as_uint(a.w) << 32) | __float_as_uint(a.z);
   a = ldq(q, 4, cap, slot);
   s.env_rel = ((unsigned long long)__float_as_uint(a.y) << 32) | __float_as_uint(a.x);
+  s.aux = __float_as_int(a.z);
   s.nact = 0;
 }
 
@@ -86,7 +89,7 @@ __device__ __forceinline__ void store_state(float4 *__restrict__ q, int cap, int
   q[(size_t)3 * cap + slot] = make_float4(s.panL, s.panR, __uint_as_float((unsigned)(s.env_start & 0xffffffffull)),
                                           __uint_as_float((unsigned)(s.env_start >> 32)));
   q[(size_t)4 * cap + slot] = make_float4(__uint_as_float((unsigned)(s.env_rel & 0xffffffffull)),
-                                          __uint_as_float((unsigned)(s.env_rel >> 32)), 0.0f, 0.0f);
+                                          __uint_as_float((unsigned)(s.env_rel >> 32)), __int_as_float(s.aux), 0.0f);
 }
 
 /* C's (int)float on x86-64 is cvttss2si: anything unrepresentable (NaN, +-Inf,
@@ -102,11 +105,13 @@ __device__ __forceinline__ int c_d2i(double v) {
 
 /* fast_pow, synth.c:140-147 */
 __device__ __forceinline__ float dev_fast_pow(float a, float b) {
-  if (a <= 0.0f) return 0.0f;
-  int ai = __float_as_int(a);
-  float t = b * __int2float_rn(ai - 1065353216);
+  /* straight-line: an early return for a <= 0 becomes a branch per frame, which ends the scheduling
+   * region of the pipelined body; the discarded lanes compute on wrapped integers, harmlessly */
+  const int ai = (int)((unsigned)__float_as_int(a) - 1065353216u);
+  float t = b * __int2float_rn(ai);
   t = t + 1065353216.0f;
-  return __int_as_float(c_f2i(t));
+  const float r = __int_as_float(c_f2i(t));
+  return (a <= 0.0f) ? 0.0f : r;
 }
 
 /* Per-block constants of one voice that the reference recomputes every sample
@@ -545,6 +550,6 @@ __global__ void k_scatter_state(float4 *__restrict__ sq, int cap, const int *__r
   s.phase = o.phase; s.finished = o.finished; s.sample = o.sample; s.sh_hold = o.sh_hold;
   s.sh_count = o.sh_count; s.x1 = o.x1; s.x2 = o.x2; s.y1 = o.y1; s.y2 = o.y2;
   s.env_active = o.env_active; s.env_vel = o.env_velocity; s.sm_gain = o.smoother_gain;
-  s.panL = o.pan_left; s.panR = o.pan_right; s.env_start = o.env_start; s.env_rel = o.env_release;
+  s.panL = o.pan_left; s.panR = o.pan_right; s.env_start = o.env_start; s.env_rel = o.env_release; s.aux = 0;
   store_state(sq, cap, slot, s);
 }

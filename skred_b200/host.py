@@ -83,7 +83,9 @@ class skb_stats(C.Structure):
                 ("n_free_voices", C.c_int32), ("n_group_voices", C.c_int32), ("n_groups", C.c_int32),
                 ("n_owned_voices", C.c_int32), ("last_render_ms", C.c_float), ("_pad", C.c_int32),
                 ("active_voice_frames", C.c_uint64), ("class_rows", C.c_uint64 * 8),
-                ("phase_cycles", C.c_uint64 * 8), ("cta_batches", C.c_uint64)]
+                ("phase_cycles", C.c_uint64 * 8), ("cta_batches", C.c_uint64),
+                ("wide_launches", C.c_uint64), ("wide_errors", C.c_uint64), ("last_wide_ms", C.c_float * 3),
+                ("_pad2", C.c_int32)]
 
 
 class SynthAPI:

@@ -87,16 +87,24 @@ def test_patch_2s_vs_oracle(n, golden_patches):
     assert_state_equal(ref.state(), gpu.state(), exact_keys=EXACT)
 
 
-def test_big_callbacks_equal_small_callbacks(luts):
-    """synth(4096) == 8 x synth(512) when no event falls inside (batch mode)."""
+def test_big_callbacks_equal_small_callbacks(luts, monkeypatch):
+    """synth(4096) == 8 x synth(512) when no event falls inside (batch mode): identical bits when both
+    run the sequential kernel; the time-split launch (SKB_WIDE=1, >= 4 windows) regroups the cross-voice
+    sum (filtered rows are mixed by pass C), so there the mix is compared within 1e-7 and the state bits."""
     wl = cases.SYNTHETIC["korg_cz_filter"](luts)
-    a, b = O.DropinCuda(64, run_seq=False), O.DropinCuda(64, run_seq=False)
-    for s in (a, b):
-        cases.drive_setup(s, wl)
-    oa = a.render(8192, block=512)
-    ob = b.render(8192, block=4096)
-    assert np.array_equal(oa.view(np.uint32), ob.view(np.uint32))
-    assert_state_equal(a.state(), b.state())
+    for wide in ("0", "1"):
+        monkeypatch.setenv("SKB_WIDE", wide)
+        a, b = O.DropinCuda(64, run_seq=False), O.DropinCuda(64, run_seq=False)
+        for s in (a, b):
+            cases.drive_setup(s, wl)
+        oa = a.render(8192, block=512)
+        ob = b.render(8192, block=4096)
+        if wide == "0":
+            assert np.array_equal(oa.view(np.uint32), ob.view(np.uint32))
+        else:
+            assert b.engine_stats().wide_launches == 2
+            assert maxdiff(oa, ob) <= 1e-7
+        assert_state_equal(a.state(), b.state())
 
 
 @pytest.mark.parametrize("name", ["lut_adsr", "korg_cz_filter", "pcm_retrigger", "misc"])
@@ -275,3 +283,48 @@ def test_run_to_run_deterministic(luts):
         _queue(s, wl["timed"])
         outs.append(s.render(3 * 4096, block=4096))
     assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+
+
+@pytest.mark.parametrize("which", ["config5_events", "korg_filter", "pcm_dense", "lut_release"])
+def test_time_split_launch_equals_sequential(which, luts, monkeypatch):
+    """With SKB_WIDE=1 a launch of >= 4 windows is rendered TIME-SPLIT (pass A: light advance + per-window snapshots,
+    pass B: one CTA per (rows, window), pass C: sequential biquad from the x scratch).  Against the
+    same engine with the split off (the default: one thread walks all windows of its voice): every
+    evolving word of every voice bit-identical, the mix within the regrouping budget of the sum."""
+    from skred_b200 import workloads as W
+    frames = 5 * 4096 + 1024 + 300                       # 8-window launches, a 2-window launch, a ragged tail
+    timed = None
+    if which == "config5_events":
+        V = 1024
+        wl = W.config5(V, seconds=600.0, luts=luts, event_seconds=frames / 44100.0 + 1.0, stationary=True)
+        timed = sorted(wl["timed"] + [(int((0.02 + 0.31 * (v % 7) / 7.0 + 0.09 * k) * 44100),
+                                       ("voice_trigger", v) if v % 3 == 2 else ("envelope_velocity", v, float(k % 2)))
+                                      for v in range(V) for k in range(4)], key=lambda x: x[0])
+    elif which == "korg_filter":
+        V = 1024
+        wl = W.config3(V, seconds=1.0)
+    elif which == "pcm_dense":
+        V = 1024
+        wl = W.config4(V, seconds=frames / 44100.0, rate_hz=40.0)
+        timed = [(t, c) for t, c in wl["timed"] if c[0] == "voice_trigger"]     # pure state edits: they ride in the launch
+    else:
+        V = 1024
+        wl = W.config2(V, seconds=1.0, luts=luts)
+        timed = [(int(0.1 * 44100) + 97 * v, ("envelope_velocity", v, 0.0)) for v in range(V)] + \
+                [(int(0.3 * 44100) + 53 * v, ("envelope_velocity", v, 1.0)) for v in range(0, V, 2)]
+    outs, states, stats = [], [], []
+    for wide in ("0", "1"):
+        monkeypatch.setenv("SKB_WIDE", wide)
+        s = O.DropinCuda(V, run_seq=False)
+        W.install(s, wl)
+        if timed:
+            _queue(s, timed)
+        outs.append(s.render(frames, block=4096))
+        states.append(s.state())
+        stats.append(s.engine_stats())
+    assert stats[0].wide_launches == 0 and stats[1].wide_launches >= 5
+    assert stats[1].wide_errors == 0
+    assert maxdiff(outs[0], outs[1]) <= 1e-6
+    assert float(np.abs(outs[0]).max()) > 1e-4
+    assert_state_equal(states[0], states[1])
+    assert stats[0].active_voice_frames == stats[1].active_voice_frames

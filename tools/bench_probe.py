@@ -33,8 +33,8 @@ for k in range(N):
     cr = [int(a - b) for a, b in zip(st.class_rows, prev.class_rows)]
     act = (st.active_voice_frames - prev.active_voice_frames) / (V * BLK)
     if k < 3 or k % 8 == 0 or k == N - 1:
-        print("launch %3d  kernel %.3f ms  active %.3f  rows/class [none none+f pw pw+f pow pow+f mixed generic] = %s" %
-              (k, st.last_render_ms, act, cr), flush=True)
+        print("launch %3d  kernel %.3f ms (A %.3f B %.3f C+reduce %.3f)  active %.3f  rows/class [none none+f pw pw+f pow pow+f mixed generic] = %s" %
+              (k, st.last_render_ms, st.last_wide_ms[0], st.last_wide_ms[1], st.last_wide_ms[2], act, cr), flush=True)
     if k == N - 1:
         nb = st.cta_batches - base.cta_batches
         print("   phase us/CTA-pass [compact setup tables prepass render wait rowsum store] since launch 16:",
@@ -61,3 +61,16 @@ rows = rows[:n * cap.value].reshape(n, cap.value)
 for c in list(np.argsort(-tot)[:4]) + list(np.argsort(tot)[:2]):
     rk = [eng.skb_debug_slot_rank(sk.engine, int(r) * 32) if r >= 0 else -1 for r in rows[c]]
     print("   CTA %3d: %.1f us (render %.1f wait %.1f)  row ranks (+8 = one-shot) %s" % (c, tot[c], us[c, 4], us[c, 5], rk))
+
+# per-warp picture of the slowest and fastest CTAs (first batch of the last launch)
+wc = np.zeros((160, 14), dtype=np.uint64)
+eng.skb_debug_warp_clocks.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+nw = eng.skb_debug_warp_clocks(sk.engine, wc.ctypes.data, 160)
+names_c = ["none", "none+f", "pw", "pw+f", "pow", "pow+f", "mixed", "generic"]
+for c in list(np.argsort(-tot)[:3]) + list(np.argsort(tot)[:3]):
+    row = []
+    for w in range(14):
+        v = int(wc[c, w])
+        cyc, dynb, nl, cl = v & ((1 << 47) - 1), (v >> 47) & 1, (v >> 48) & 0xff, (v >> 56) & 0xff
+        row.append("w%d(s%d):%s%s/%d=%.0fus" % (w, w % 4, names_c[cl] if cl < 8 else "-", "*" if dynb else "", nl, cyc / 1965.0))
+    print("   CTA %3d %.1f us: %s" % (c, tot[c], "  ".join(row)))
