@@ -215,6 +215,15 @@ int  skb_finish(skb_engine *e, const float *d_mix, int nframes, const float *gai
  * split form that do not bring one: synth() renders the event-free segments of one call into
  * it back to back and finishes once (one synchronisation per call, not per segment). */
 float *skb_mix_buffer(skb_engine *e);
+/* Per-voice stereo tap: the `user` buffer of synth() (synth.c:503-511, 533-611; skred.c:120-131 records
+ * from it).  While enabled, every render also leaves tap[frame][voice][L, R] — each voice's contribution to
+ * the mix before the master volume, zeros for skipped (finished, amp == 0), disconnected and not-owned
+ * voices — in device memory, frames counted from the last skb_finish (at most max_frames of them).
+ * skb_read_tap copies frames [frame0, frame0 + nframes) to out[nframes][n_voices][2] on the host; call it
+ * after skb_finish.  The tap moves 8 bytes per voice-sample (256 MiB per 512-frame block at
+ * 65,536 voices), so it is off until asked for; time-split launches are not used while it is on. */
+int  skb_set_tap(skb_engine *e, int enable);
+int  skb_read_tap(skb_engine *e, int frame0, int nframes, float *out);
 /* Wait for everything queued on `stream` (NULL = engine stream). */
 int  skb_sync(skb_engine *e, void *stream);
 

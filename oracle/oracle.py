@@ -71,6 +71,32 @@ class HarnessSkred(SynthAPI):
     def sync_state(self):
         self.lib.ref_sync_state()
 
+    def enable_tap(self, frames=BLOCK):
+        """Per-voice tap `user` of synth() (synth.c:503-511, 533-611) sized for callbacks of up to
+        `frames` frames; call before the first render.  Returns a [frames][voice][L,R] view that every
+        callback overwrites from frame 0."""
+        self.lib.ref_enable_tap.restype = C.c_void_p
+        self.lib.ref_enable_tap.argtypes = [C.c_int]
+        p = self.lib.ref_enable_tap(frames)
+        buf = (C.c_float * (frames * self.voice_max * 2)).from_address(p)
+        self._tap = np.ctypeslib.as_array(buf).reshape(frames, self.voice_max, 2)
+        return self._tap
+
+    def render_with_tap(self, nframes, block=BLOCK, events=None):
+        """render(), collecting the tap of every callback: (out[nframes][2], tap[nframes][voice][2])."""
+        out = np.zeros((nframes, 2), dtype=np.float32)
+        taps = np.zeros((nframes, self.voice_max, 2), dtype=np.float32)
+        done, k = 0, 0
+        while done < nframes:
+            n = min(block, nframes - done)
+            if events and k in events:
+                self.apply(events[k])
+            self._synth(out[done:done + n], n)
+            taps[done:done + n] = self._tap[:n]
+            done += n
+            k += 1
+        return out, taps
+
     def engine_stats(self):
         """skb_stats of the engine behind a drop-in build (port: linked in; cuda: libskred_b200.so)."""
         from skred_b200.host import skb_stats

@@ -63,6 +63,7 @@ float *mw_free(float *f) { free(f); return NULL; }
 
 /* ---- 2. offline driver ------------------------------------------------- */
 static float *g_tap = NULL;
+static int g_tap_frames = 0;
 static wire_t g_wire = WIRE();
 
 int ref_voice_max(void) { return VOICE_MAX; }
@@ -74,7 +75,11 @@ void ref_init(void) {
   once = 1;
   /* the per-voice tap `user` must hold num_frames*VOICE_MAX*2 floats
    * (synth.c:533-611); it is latched on the first synth() call. */
-  g_tap = (float *)calloc((size_t)SYNTH_FRAMES_PER_CALLBACK * VOICE_MAX * 2, sizeof(float));
+#ifndef SKB_DROPIN
+  /* synth.c writes it unconditionally; the drop-in treats NULL as "no tap" (ref_enable_tap) */
+  g_tap_frames = SYNTH_FRAMES_PER_CALLBACK;
+  g_tap = (float *)calloc((size_t)g_tap_frames * VOICE_MAX * 2, sizeof(float));
+#endif
   synth_init();
   wave_table_init();
   voice_init();
@@ -84,6 +89,16 @@ void ref_init(void) {
 }
 
 float *ref_tap(void) { return g_tap; }
+int ref_tap_frames(void) { return g_tap_frames; }
+
+/* Size the per-voice tap for callbacks of up to `frames` frames.  Call before the first
+ * ref_render: synth() latches the pointer on its first call (synth.c:503-511). */
+float *ref_enable_tap(int frames) {
+  free(g_tap);
+  g_tap_frames = frames;
+  g_tap = (float *)calloc((size_t)frames * VOICE_MAX * 2, sizeof(float));
+  return g_tap;
+}
 
 /* Feed one line of skode to the reference parser (wire.c:924). */
 int ref_wire(const char *line) {

@@ -45,6 +45,8 @@ struct skb_engine {
   skb_op *ops;
   int n_ops, cap_ops;
   float *mix;           /* scratch for skb_render */
+  float *tap;           /* per-voice tap [max_frames][n][2] (synth.c:533-611), NULL = off */
+  int tap_cursor;       /* frames rendered since the last skb_finish */
   int err;
   char errtxt[256];
   skb_stats stats;
@@ -82,7 +84,7 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
 void skb_destroy(skb_engine *e) {
   if (!e) return;
   for (int i = 0; i < e->n_tables; i++) free(e->tables[i].data);
-  free(e->tables); free(e->par); free(e->st); free(e->owner); free(e->ops); free(e->mix);
+  free(e->tables); free(e->par); free(e->st); free(e->owner); free(e->ops); free(e->mix); free(e->tap);
   free(e);
 }
 
@@ -305,9 +307,12 @@ int skb_render_mix(skb_engine *e, int nframes, uint64_t ssc, const float *noise,
   ensure_owner(e);
   flush_ops(e);
   const int rank = e->cfg.rank;
+  if (e->tap && e->tap_cursor + nframes > e->cfg.max_frames) return fail(e, SKB_ERR_ARG, "render_mix: tap overflow");
   for (int i = 0; i < nframes; i++) {
     ssc++;                                                        /* :521 */
     float L = 0.0f, R = 0.0f;
+    float *tap = e->tap ? e->tap + (size_t)(e->tap_cursor + i) * e->n * 2 : NULL;
+    if (tap) memset(tap, 0, (size_t)e->n * 2 * sizeof(float));   /* :534-541, 609-611 */
     const float white = noise ? noise[i] : 0.0f;                  /* :525 */
     for (int n = 0; n < e->n; n++) {                              /* :526 */
       if (e->owner[n] != rank) continue;                          /* other shard (components never straddle) */
@@ -366,12 +371,28 @@ int skb_render_mix(skb_engine *e, int nframes, uint64_t ssc, const float *noise,
         float r = s->sample * s->pan_right;
         L += l;
         R += r;
+        if (tap) { tap[2 * n] = l; tap[2 * n + 1] = r; }          /* :607-608 */
       }
     }
     mix[2 * i + 0] = L;
     mix[2 * i + 1] = R;
   }
   e->stats.frames_rendered += (uint64_t)nframes;
+  if (e->tap) e->tap_cursor += nframes;
+  return e->err;
+}
+
+int skb_set_tap(skb_engine *e, int enable) {
+  if (!e) return SKB_ERR_ARG;
+  if (enable && !e->tap) e->tap = (float *)calloc((size_t)e->cfg.max_frames * e->n * 2, sizeof(float));
+  if (!enable) { free(e->tap); e->tap = NULL; }
+  e->tap_cursor = 0;
+  return e->err;
+}
+
+int skb_read_tap(skb_engine *e, int frame0, int nframes, float *out) {
+  if (!e || !out || !e->tap || frame0 < 0 || nframes < 0 || frame0 + nframes > e->cfg.max_frames) return SKB_ERR_ARG;
+  memcpy(out, e->tap + (size_t)frame0 * e->n * 2, (size_t)nframes * e->n * 2 * sizeof(float));
   return e->err;
 }
 
@@ -385,6 +406,7 @@ int skb_finish(skb_engine *e, const float *mix, int nframes, const float *gain,
     out[(size_t)i * num_channels + 0] = mix[2 * i + 0] * gain[i];
     out[(size_t)i * num_channels + 1] = mix[2 * i + 1] * gain[i];
   }
+  e->tap_cursor = 0;
   return e->err;
 }
 

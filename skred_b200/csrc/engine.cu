@@ -78,6 +78,13 @@ struct skb_engine {
   float *d_xs = nullptr; size_t xs_cap = 0;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr;
 
+  /* per-voice tap (synth.c:533-611) */
+  bool tap_on = false, vos_dirty = true;
+  int tap_cursor = 0;                               /* frames rendered since the last skb_finish */
+  float2 *d_tap = nullptr; size_t tap_cap = 0;      /* [max_frames][n] */
+  int *d_vos = nullptr; size_t vos_cap = 0;          /* voice of slot */
+  float2 *h_tap = nullptr; size_t h_tap_cap = 0;
+
   /* device */
   float4 *d_pq = nullptr, *d_sq[2] = {nullptr, nullptr};
   int cur = 0;
@@ -121,6 +128,7 @@ struct skb_engine {
     std::vector<skb_op> ops;            /* op.voice = slot */
     std::vector<uint32_t> wake;         /* bit per slot touched by an op of the batch */
     std::vector<int> wake_words;        /* ... and which words are non-zero */
+    int tap_frame0 = 0;                 /* first frame of the batch in the tap buffer (= its offset in the caller's mix) */
   } batch;
   int *d_win = nullptr, *h_win = nullptr; size_t win_cap = 0, h_win_cap = 0;
   skb_op *d_bops = nullptr, *h_bops = nullptr; size_t bops_cap = 0, h_bops_cap = 0;
@@ -221,6 +229,8 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
             cudaEventCreate(&e->ev_a) == cudaSuccess && cudaEventCreate(&e->ev_b) == cudaSuccess &&
             cudaFuncSetAttribute(k_render_free, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)skb_free_smem_bytes()) == cudaSuccess &&
+            cudaFuncSetAttribute(k_render_free_tap, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)skb_free_smem_bytes()) == cudaSuccess &&
             cudaFuncSetAttribute(k_render_window, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)skb_free_smem_bytes()) == cudaSuccess &&
             cudaFuncSetAttribute(k_render_biquad, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -257,6 +267,7 @@ void skb_destroy(skb_engine *e) {
   cudaFree(e->d_envbuf); cudaFree(e->d_ctarows); cudaFree(e->d_ctaphase);
   cudaFree(e->d_win); cudaFree(e->d_bops); cudaFree(e->d_wake);
   cudaFree(e->d_lists); cudaFree(e->d_xrow); cudaFree(e->d_snap); cudaFree(e->d_xs);
+  cudaFree(e->d_tap); cudaFree(e->d_vos); cudaFreeHost(e->h_tap);
   if (e->ev_a) cudaEventDestroy(e->ev_a);
   if (e->ev_b) cudaEventDestroy(e->ev_b);
   cudaFreeHost(e->h_win); cudaFreeHost(e->h_bops); cudaFreeHost(e->h_wake);
@@ -563,6 +574,7 @@ static int replan(skb_engine *e, cudaStream_t st) {
       cudaError_t rr = grow_dev(&e->d_xrow, &e->xrow_cap, xrow.size());
       if (rr != cudaSuccess) return fail(e, SKB_ERR_CUDA, "x row map alloc", cudaGetErrorString(rr));
       CK(cudaMemcpyAsync(e->d_xrow, xrow.data(), xrow.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+      e->vos_dirty = true;                       /* (the bins' slots are assigned further down) */
       if (!lists.empty()) {
         rr = grow_dev(&e->d_lists, &e->lists_cap, lists.size());
         if (rr != cudaSuccess) return fail(e, SKB_ERR_CUDA, "row list alloc", cudaGetErrorString(rr));
@@ -804,7 +816,7 @@ static int batch_launch(skb_engine *e) {
   CK(cudaEventRecord(e->ev_h2d, st));
   /* time-split launch?  Needs enough windows to split, eligible rows, and no modulation bins */
   const bool wide = e->n_wide_rows > 0 && nwin >= SKB_WIDE_MIN_WIN && nwin < (int)e->list_b.size() &&
-                    e->list_b[nwin].ctas > 0 && e->bins.empty() && (e->cfg.flags & SKB_CFG_WIDE);
+                    e->list_b[nwin].ctas > 0 && e->bins.empty() && (e->cfg.flags & SKB_CFG_WIDE) && !e->tap_on;
   const skb_engine::RowList lb = wide ? e->list_b[nwin] : skb_engine::RowList();
   const int groups_b = wide ? lb.ctas * (lb.rows_cap / SKB_CTA_WARPS) : 0;
   const int groups_c = (wide && e->list_c.ctas > 0) ? e->list_c.ctas * (e->list_c.rows_cap / SKB_CTA_WARPS) : 0;
@@ -814,6 +826,17 @@ static int batch_launch(skb_engine *e) {
     CK(cudaStreamSynchronize(st));
     r = grow_dev(&e->d_partials, &e->partials_cap, n_prow * (size_t)e->cfg.max_frames);
     if (r != cudaSuccess) return fail(e, SKB_ERR_CUDA, "partials alloc", cudaGetErrorString(r));
+  }
+  if (e->tap_on) {
+    if (e->vos_dirty) {
+      r = grow_dev(&e->d_vos, &e->vos_cap, (size_t)e->cap);
+      if (r != cudaSuccess) return fail(e, SKB_ERR_CUDA, "tap slot map alloc", cudaGetErrorString(r));
+      CK(cudaMemcpyAsync(e->d_vos, e->voice_of_slot.data(), (size_t)e->cap * sizeof(int), cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));            /* pageable source */
+      e->vos_dirty = false;
+    }
+    /* skipped, disconnected and not-owned voices read 0 (synth.c:534-541, 609-611) */
+    CK(cudaMemsetAsync(e->d_tap + (size_t)e->batch.tap_frame0 * e->n, 0, (size_t)nframes * e->n * sizeof(float2), st));
   }
   CK(cudaEventRecord(e->ev_t0, st));
   if (e->n_free_rows > 0) {
@@ -832,11 +855,13 @@ static int batch_launch(skb_engine *e) {
     fa.snap = e->d_snap; fa.snap_nwin = e->snap_nwin;
     fa.xs = e->d_xs; fa.xs_frames = e->cfg.max_frames; fa.xrow_of = e->d_xrow;
     fa.cpw = 0; fa.group0 = 0;
+    fa.tap = e->tap_on ? e->d_tap + (size_t)e->batch.tap_frame0 * e->n : nullptr; fa.voice_of_slot = e->d_vos; fa.tap_n = e->tap_on ? e->n : 0;
     { const char *pp = getenv("SKB_PHASE_PASS"); fa.phase_pass = pp ? atoi(pp) : 0; }
     fa.warp_diag = e->d_ctaphase ? e->d_ctaphase + (size_t)e->n_sm * 8 : nullptr;
     if (wide)       /* "no snapshot" = finished: group 0 of every window's snapshot */
       CK(cudaMemsetAsync(e->d_snap, 0x01, (size_t)nwin * e->cap * sizeof(float4), st));
-    k_render_free<<<e->free_ctas, SKB_CTA_THREADS, skb_free_smem_bytes(), st>>>(fa);
+    if (e->tap_on) k_render_free_tap<<<e->free_ctas, SKB_CTA_THREADS, skb_free_smem_bytes(), st>>>(fa);
+    else k_render_free<<<e->free_ctas, SKB_CTA_THREADS, skb_free_smem_bytes(), st>>>(fa);
     e->stats.kernel_launches++;
     if (wide) {
       CK(cudaEventRecord(e->ev_a, st));
@@ -862,7 +887,9 @@ static int batch_launch(skb_engine *e) {
     const size_t smem = (size_t)3 * nt * sizeof(float) + (size_t)2 * (nt / 32) * sizeof(float2);
     k_render_bins<<<(int)e->bins.size(), nt, smem, st>>>(e->d_pq, e->d_sq[e->cur], e->cap, e->d_bins, e->d_tables,
                                                          e->d_noise, nframes, (unsigned long long)e->batch.ssc0,
-                                                         e->d_partials, nframes, e->d_counters + 1);
+                                                         e->d_partials, nframes, e->d_counters + 1,
+                                                         e->tap_on ? e->d_tap + (size_t)e->batch.tap_frame0 * e->n : nullptr, e->d_vos,
+                                                         e->tap_on ? e->n : 0);
     e->stats.kernel_launches++;
   }
   if (n_prows_now > 0) {
@@ -892,6 +919,8 @@ int skb_render_mix(skb_engine *e, int nframes, uint64_t ssc_before, const float 
                    float *d_mix, void *stream) {
   if (!e) return SKB_ERR_ARG;
   if (nframes < 0 || nframes > e->cfg.max_frames || !d_mix) return fail(e, SKB_ERR_ARG, "render_mix: bad argument");
+  if (e->tap_on && e->tap_cursor + nframes > e->cfg.max_frames)
+    return fail(e, SKB_ERR_ARG, "render_mix: tap on and more than max_frames rendered since the last skb_finish");
   cudaSetDevice(e->cfg.device);
   cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
   if (e->err) return e->err;
@@ -910,6 +939,7 @@ int skb_render_mix(skb_engine *e, int nframes, uint64_t ssc_before, const float 
     if (sync_inputs(e, st)) return e->err;        /* plan, parameter records, ops -> k_apply_ops */
     if (nframes == 0) return e->err;
     e->batch.open = true; e->batch.st = st; e->batch.mix = d_mix; e->batch.frames = 0; e->batch.ssc0 = ssc_before;
+    e->batch.tap_frame0 = e->tap_cursor;
     e->batch.win_frames.clear(); e->batch.win_ob.clear(); e->batch.ops.clear();
     if (e->batch.wake.size() < ((size_t)e->cap + 31) / 32) e->batch.wake.assign(((size_t)e->cap + 31) / 32, 0u);
   } else if (nframes == 0) {
@@ -941,6 +971,7 @@ int skb_render_mix(skb_engine *e, int nframes, uint64_t ssc_before, const float 
     e->batch.win_frames.push_back(std::min(SKB_ENV_WIN, nframes - done));
   }
   e->batch.frames += nframes;
+  if (e->tap_on) e->tap_cursor += nframes;
   e->stats.frames_rendered += (uint64_t)nframes;
   if (!e->bins.empty() || (e->cfg.flags & SKB_CFG_NO_BATCH)) return batch_launch(e);
   return e->err;
@@ -970,6 +1001,7 @@ int skb_finish(skb_engine *e, const float *d_mix, int nframes, const float *gain
   for (int i = 0; i < 8; i++) e->stats.phase_cycles[i] = e->h_counters[10 + i];
   e->stats.cta_batches = e->h_counters[18];
   e->stats.wide_errors = e->h_counters[19];
+  e->tap_cursor = 0;
   if (num_channels == 2) {
     memcpy(out, e->h_out, (size_t)nframes * sizeof(float2));
   } else {
@@ -1012,6 +1044,35 @@ int skb_render(skb_engine *e, int nframes, uint64_t ssc_before, const float *gai
 }
 
 float *skb_mix_buffer(skb_engine *e) { return e ? (float *)e->d_mix : nullptr; }
+
+int skb_set_tap(skb_engine *e, int enable) {
+  if (!e) return SKB_ERR_ARG;
+  cudaSetDevice(e->cfg.device);
+  if (batch_launch(e)) return e->err;
+  if (enable && !e->d_tap) {
+    const size_t need = (size_t)e->cfg.max_frames * e->n;
+    if (need * sizeof(float2) > ((size_t)16 << 30))
+      return fail(e, SKB_ERR_CAPACITY, "tap: max_frames x voices x 8 bytes exceeds 16 GiB; create the engine with a smaller max_frames");
+    cudaError_t r = grow_dev(&e->d_tap, &e->tap_cap, need);
+    if (r != cudaSuccess) return fail(e, SKB_ERR_CUDA, "tap alloc", cudaGetErrorString(r));
+  }
+  e->tap_on = enable != 0;
+  e->tap_cursor = 0;
+  return e->err;
+}
+
+int skb_read_tap(skb_engine *e, int frame0, int nframes, float *out) {
+  if (!e || !out || frame0 < 0 || nframes < 0 || frame0 + nframes > e->cfg.max_frames) return fail(e, SKB_ERR_ARG, "read_tap: bad argument");
+  if (!e->tap_on || !e->d_tap) return fail(e, SKB_ERR_STATE, "read_tap: the tap is off");
+  if (nframes == 0) return e->err;
+  cudaSetDevice(e->cfg.device);
+  if (batch_launch(e)) return e->err;
+  cudaStream_t st = e->last_stream ? e->last_stream : e->stream;
+  /* straight into the caller's (pageable) buffer: the copy is as large as the tap itself */
+  CK(cudaMemcpyAsync(out, e->d_tap + (size_t)frame0 * e->n, (size_t)nframes * e->n * sizeof(float2), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return e->err;
+}
 
 int skb_sync(skb_engine *e, void *stream) {
   if (!e) return SKB_ERR_ARG;

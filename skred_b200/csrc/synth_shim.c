@@ -1056,9 +1056,17 @@ static int next_firing_boundary(int done, int num_frames, uint64_t start_count) 
 }
 
 void synth(float *buffer, float *input, int num_frames, int num_channels, void *user) {
-  (void)input; (void)user;   /* the per-voice tap `user` is opt-in: see skb_shim_* docs */
+  (void)input;
+  /* `user`: the per-voice tap one_skred_frame[frame][voice][L,R], latched on the FIRST call only like the
+   * reference does (synth.c:503-511).  NULL = no tap (the reference would fault; skred.c always passes one). */
   static int first = 1;
-  if (first) { synth_frames_per_callback = num_frames; first = 0; }
+  static float *tap_user = NULL;
+  if (first) {
+    synth_frames_per_callback = num_frames;
+    tap_user = (float *)user;
+    first = 0;
+    if (tap_user && skb_set_tap(engine(), 1) != SKB_OK) shim_die("skb_set_tap");
+  }
   const int slot = (int)(g_bench_n % SHIM_BENCH_SLOTS);
   clock_gettime(CLOCK_MONOTONIC, &g_bench[slot].a);
   g_bench[slot].frames = num_frames; g_bench[slot].order = g_bench_n; g_bench[slot].state = 1;
@@ -1096,6 +1104,8 @@ void synth(float *buffer, float *input, int num_frames, int num_channels, void *
     }
     if (skb_finish(g_engine, d_mix, chunk1 - chunk0, g_gain, buffer + (size_t)chunk0 * num_channels, num_channels, NULL) != SKB_OK)
       shim_die("skb_finish");
+    if (tap_user && skb_read_tap(g_engine, 0, chunk1 - chunk0, tap_user + (size_t)chunk0 * VOICE_MAX * 2) != SKB_OK)
+      shim_die("skb_read_tap");                    /* synth.c:533-611 */
     g_gain_fill = 0;
   }
   clock_gettime(CLOCK_MONOTONIC, &g_bench[slot].b);

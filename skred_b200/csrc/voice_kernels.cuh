@@ -353,7 +353,8 @@ k_render_bins(const float4 *__restrict__ pq, float4 *__restrict__ sq, int cap,
               const skb_bin_desc *__restrict__ bins,
               const float *__restrict__ tables, const float *__restrict__ noise,
               int nframes, unsigned long long ssc_before,
-              float2 *__restrict__ partials, int row_stride, unsigned long long *__restrict__ counter) {
+              float2 *__restrict__ partials, int row_stride, unsigned long long *__restrict__ counter,
+              float2 *__restrict__ tap, const int *__restrict__ voice_of_slot, int tap_n) {
   extern __shared__ float bsm[];
   const skb_bin_desc bd = bins[blockIdx.x];
   const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
@@ -370,6 +371,8 @@ k_render_bins(const float4 *__restrict__ pq, float4 *__restrict__ sq, int cap,
   incs[tid] = live ? p.inc : 0.0f;
   const bool wants_noise = live && (p.flags & SKB_F_NOISE);
   float2 *out_row = partials + (size_t)bd.row * row_stride;
+  float2 *tap_lane = nullptr;                      /* per-voice tap, synth.c:533-611 */
+  if (tap_n && live) { const int tv = __ldg(voice_of_slot + slot); if (tv >= 0) tap_lane = tap + tv; }
   __syncthreads();
   for (int f = 0; f < nframes; f++) {
     BinMods mod;
@@ -386,6 +389,7 @@ k_render_bins(const float4 *__restrict__ pq, float4 *__restrict__ sq, int cap,
       }
       __syncthreads();
     }
+    if (tap_lane) tap_lane[(size_t)f * tap_n] = o;
     /* fixed-order sum: xor butterfly inside the warp, then warps in order */
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {

@@ -328,3 +328,38 @@ def test_time_split_launch_equals_sequential(which, luts, monkeypatch):
     assert float(np.abs(outs[0]).max()) > 1e-4
     assert_state_equal(states[0], states[1])
     assert stats[0].active_voice_frames == stats[1].active_voice_frames
+
+
+@pytest.mark.parametrize("which", ["patch0_fm", "patch42", "korg_cz_filter", "pcm_retrigger", "misc"])
+def test_voice_tap_matches_reference(which, luts, golden_patches):
+    """synth()'s `user` buffer (synth.c:503-511, 533-611; skred.c:120-131 records from it): per frame and
+    voice the (left, right) added to the mix, zeros for skipped / disconnected voices.  Each value is one
+    voice's own arithmetic, so the tap is compared BIT FOR BIT — pipelined rows, generic rows and
+    modulation bins (patch 0 is FM) alike; the second half of the run uses 2,048-frame calls."""
+    if which.startswith("patch"):
+        V = 64
+        ref, gpu = O.RefSkred(V), O.DropinCuda(V)
+        n = 0 if which == "patch0_fm" else 42
+        for s in (ref, gpu):
+            s.load_lines(patch_lines(golden_patches, n))
+        drive = None
+    else:
+        wl = cases.SYNTHETIC[which](luts)
+        V = wl["voices"]
+        ref, gpu = O.RefSkred(V, run_seq=False), O.DropinCuda(V, run_seq=False)
+        for s in (ref, gpu):
+            cases.drive_setup(s, wl)
+        drive = wl.get("events")
+    ref.enable_tap(512)
+    gpu.enable_tap(2048)
+    oa, ta = ref.render_with_tap(8 * 512, events=drive)
+    ob, tb = gpu.render_with_tap(8 * 512, events=drive)
+    assert maxdiff(oa, ob) <= FULL_SCALE_TOL
+    assert np.array_equal(ta.view(np.uint32), tb.view(np.uint32))
+    if drive is not None and all(k < 8 for k in drive):
+        # (not the patches: their sequencer fires per callback, so the callback size is part of the input, F8)
+        oa2, ta2 = ref.render_with_tap(4096)
+        ob2, tb2 = gpu.render_with_tap(4096, block=2048)
+        assert maxdiff(oa2, ob2) <= FULL_SCALE_TOL
+        assert np.array_equal(ta2.view(np.uint32), tb2.view(np.uint32))
+    assert float(np.abs(ta).max()) > 0.0

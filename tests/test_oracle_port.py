@@ -91,3 +91,21 @@ def test_port_matches_reference_bench_workload_1024(luts):
     n = b.engine_stats().active_voice_frames
     # two thirds of the voices always render, the one-shot third only while a sample plays
     assert 2 * V // 3 * frames <= n < V * frames
+
+
+@needs_ref
+@pytest.mark.parametrize("n", [0, 15, 42])
+def test_port_tap_matches_reference(n, golden_patches):
+    """The per-voice tap `user` of synth() (synth.c:533-611): [frame][voice][L,R] before the master
+    volume, zeros for skipped / disconnected voices — bit for bit, through the drop-in shim."""
+    a, b = O.RefSkred(64), O.PortSkred(64)
+    a.enable_tap(512)
+    b.enable_tap(512)
+    lines = patch_lines(golden_patches, n)
+    a.load_lines(lines)
+    b.load_lines(lines)
+    oa, ta = a.render_with_tap(20 * 512)
+    ob, tb = b.render_with_tap(20 * 512)
+    assert np.array_equal(oa.view(np.uint32), ob.view(np.uint32))
+    assert np.array_equal(ta.view(np.uint32), tb.view(np.uint32))
+    assert float(np.abs(ta).max()) > 0.0
