@@ -62,6 +62,13 @@ def load_peaks():
     return 6650.0, 1965.0, "fallback"
 
 
+def load_ncu_counters():
+    """Per-launch counters of the dominant kernel from the committed ncu capture of this same command
+    (profiles/): DRAM bytes for roofline.traffic, warp instructions for the issue-slot roofline."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_counters.json")
+    return json.load(open(p)) if os.path.exists(p) else None
+
+
 def load_luts():
     p = os.path.join(ROOT, "tests", "golden", "notamy_luts.npz")
     return dict(np.load(p)) if os.path.exists(p) else None
@@ -359,6 +366,9 @@ def own_arm(a):
     alive_pcm = max(0.0, alive_per_launch - 2.0 * owned / 3.0)
     flops_vs = (owned / 3.0 * 15.0 + owned / 3.0 * 32.0 + alive_pcm * 15.0) / max(alive_per_launch, 1.0)
     ach_flops = k_act * flops_vs / (k_ms * 1e-3)
+    ncu = load_ncu_counters() if (V == 65536 and F == 4096 and world == 1) else None
+    traffic = float(ncu["dram_bytes_read"] + ncu["dram_bytes_write"]) if ncu else None
+    issue_peak = N_SM * 4 * sm_mhz * 1e6                     # warp instructions per second: 4 schedulers per SM
 
     if rank == 0:
         line = {
@@ -374,12 +384,18 @@ def own_arm(a):
                        "launches": "the engine renders the %d callbacks of a step in one launch; events are applied in-kernel at the 512-frame boundaries" % (F // LF),
                        "l2": "state+params %.1f MB per launch, each word touched once per launch (no reuse to cache)" % (owned * 276 / 1e6)},
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                         "traffic": None, "peak_kind": peak_kind, "kernel": "k_render_free(+k_render_bins,+k_reduce_rows)",
+                         "traffic": traffic, "peak_kind": peak_kind, "kernel": "k_render_free(+k_render_bins,+k_reduce_rows)",
                          "kernel_ms": k_ms,
                          "note": "the path is FP32-issue bound, not HBM bound (SURVEY 8d): see roofline_fp32"},
             "roofline_fp32": {"bound": "fp32-issue (no FMA: parity mode rounds every op)", "achieved": ach_flops / 1e12,
                               "peak": fp32_peak / 1e12, "unit": "Tflop/s (1 op per lane-issue)",
                               "frac": ach_flops / fp32_peak, "flops_per_voice_sample": flops_vs},
+            "roofline_issue": None if not ncu else {
+                "bound": "warp-instruction issue slots (4 schedulers x %d SMs x SM clock)" % N_SM,
+                "achieved": ncu["warp_instructions"] / (k_ms * 1e-3) / 1e12, "peak": issue_peak / 1e12,
+                "unit": "T warp-instructions/s", "frac": ncu["warp_instructions"] / (k_ms * 1e-3) / issue_peak,
+                "warp_instructions_per_launch": ncu["warp_instructions"],
+                "note": "instruction count from the committed ncu capture of this command (profiles/r01_ncu_counters.json), duration measured live"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s / a.steps * 1e3, "api": "synth(buffer, NULL, %d, 2, NULL)" % F},
             "gpu_launches": launches,

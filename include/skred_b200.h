@@ -159,6 +159,8 @@ typedef struct skb_config {
  * parallel, pass C runs the biquads).  Bit-identical state, same mix within the regrouping of the sum; measured
  * on B200 it does not pay (profiles/r01_time_split.txt), so the default is the sequential kernel. */
 #define SKB_CFG_WIDE 4u
+/* measuring aid: deal rows to CTAs by cost only (plain LPT) instead of class-affine (engine.cu: replan) */
+#define SKB_CFG_NO_AFFINE 8u
 
 int  skb_create(skb_engine **out, const skb_config *cfg);
 void skb_destroy(skb_engine *e);

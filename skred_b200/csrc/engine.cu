@@ -511,23 +511,62 @@ static int replan(skb_engine *e, cudaStream_t st) {
         if (filt) xrow[r] = e->n_xrows++;
       }
     }
-    /* deal `items` = (cost, row entry) to at most max_ctas CTAs; returns [ctas][rows_cap], -1 padded */
-    auto deal = [](std::vector<std::pair<int, int>> items, int max_ctas, std::vector<int> &out, int *ctas_out, int *cap_out) {
+    /* deal `items` = (cost, row entry) to at most max_ctas CTAs; returns [ctas][rows_cap], -1 padded.
+     * rank != nullptr: CLASS-AFFINE dealing.  Every distinct loop body a CTA's warps run is code its SM
+     * must keep streaming (each body is 3-6 KB of SASS; one more body per SM measured -20 %,
+     * profiles/r01_s4_ab.txt), so the rows of a costly class (CZ and / or filter) go to a subset of the
+     * CTAs sized by the class's share of the costly work — a CTA then renders ONE costly class — and the
+     * light rows (plain, one-shot) fill every CTA up by LPT as before. */
+    auto deal = [](std::vector<std::pair<int, int>> items, int max_ctas, std::vector<int> &out, int *ctas_out, int *cap_out,
+                   const std::vector<int> *rank) {
       const int n = (int)items.size();
       const int ctas = std::max(1, std::min(max_ctas, n));
       const int nb = n ? ((n + ctas - 1) / ctas + SKB_CTA_WARPS - 1) / SKB_CTA_WARPS : 0;
       const int rcap = nb * SKB_CTA_WARPS;
       std::stable_sort(items.begin(), items.end(), [](const std::pair<int, int> &x, const std::pair<int, int> &y) { return x.first > y.first; });
-      typedef std::pair<long long, int> Load;                                /* (load, cta) */
-      std::priority_queue<Load, std::vector<Load>, std::greater<Load>> pqd;
-      for (int c = 0; c < ctas; c++) pqd.push(Load(0, c));
       std::vector<std::vector<std::pair<int, int>>> mine((size_t)ctas);
-      for (size_t i = 0; i < items.size(); i++) {
-        Load l = pqd.top(); pqd.pop();
-        mine[l.second].push_back(items[i]);
-        l.first += items[i].first;
-        if ((int)mine[l.second].size() < rcap) pqd.push(l);                /* a full CTA leaves the heap */
+      std::vector<long long> load((size_t)ctas, 0);
+      /* LPT of `sub` over CTAs [c0, c1) on top of the current loads */
+      auto lpt = [&](const std::vector<std::pair<int, int>> &sub, int c0, int c1) {
+        typedef std::pair<long long, int> Load;                              /* (load, cta) */
+        std::priority_queue<Load, std::vector<Load>, std::greater<Load>> pqd;
+        for (int c = c0; c < c1; c++) if ((int)mine[c].size() < rcap) pqd.push(Load(load[c], c));
+        std::vector<std::pair<int, int>> left;
+        for (size_t i = 0; i < sub.size(); i++) {
+          if (pqd.empty()) { left.push_back(sub[i]); continue; }
+          Load l = pqd.top(); pqd.pop();
+          mine[l.second].push_back(sub[i]);
+          l.first += sub[i].first; load[l.second] = l.first;
+          if ((int)mine[l.second].size() < rcap) pqd.push(l);                /* a full CTA leaves the heap */
+        }
+        return left;
+      };
+      const int HEAVY = 29;                                                  /* cost_of_rank of anything with CZ or a filter */
+      std::vector<std::pair<int, int>> light;
+      if (rank && ctas >= 8) {
+        std::vector<std::vector<std::pair<int, int>>> byc(8);
+        long long hsum = 0, csum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (size_t i = 0; i < items.size(); i++) {
+          const int rk = (*rank)[items[i].second & ~SKB_ROW_WIDE] & 7;
+          if (items[i].first >= HEAVY) { byc[rk].push_back(items[i]); csum[rk] += items[i].first; hsum += items[i].first; }
+          else light.push_back(items[i]);
+        }
+        int c0 = 0, nheavy = 0, seen = 0;
+        for (int rk = 7; rk >= 0; rk--) nheavy += byc[rk].empty() ? 0 : 1;
+        for (int rk = 7; rk >= 0; rk--) {
+          if (byc[rk].empty()) continue;
+          seen++;
+          int k = (seen == nheavy) ? ctas - c0 : (int)((double)ctas * (double)csum[rk] / (double)hsum + 0.5);
+          k = std::max(1, std::min(k, ctas - c0 - (nheavy - seen)));
+          std::vector<std::pair<int, int>> left = lpt(byc[rk], c0, c0 + k);
+          light.insert(light.end(), left.begin(), left.end());              /* (did not fit: anywhere) */
+          c0 += k;
+        }
+        std::stable_sort(light.begin(), light.end(), [](const std::pair<int, int> &x, const std::pair<int, int> &y) { return x.first > y.first; });
+      } else {
+        light = items;
       }
+      lpt(light, 0, ctas);
       out.assign((size_t)std::max(ctas * rcap, 1), -1);
       for (int c = 0; c < ctas; c++) {
         std::stable_sort(mine[c].begin(), mine[c].end(), [](const std::pair<int, int> &x, const std::pair<int, int> &y) {
@@ -536,9 +575,10 @@ static int replan(skb_engine *e, cudaStream_t st) {
       }
       *ctas_out = n ? ctas : 0; *cap_out = rcap;
     };
+    const std::vector<int> *affine = (e->cfg.flags & SKB_CFG_NO_AFFINE) ? nullptr : &row_rank;
     std::vector<std::pair<int, int>> items((size_t)nrows);
     for (int r = 0; r < nrows; r++) items[r] = std::make_pair(row_cost[r], r);
-    deal(items, e->n_sm, ctarows, &e->free_ctas, &e->rows_cap);
+    deal(items, e->n_sm, ctarows, &e->free_ctas, &e->rows_cap, affine);
     e->free_groups = e->free_ctas * (e->rows_cap / SKB_CTA_WARPS);
     /* pass A of a time-split launch: the same rows, the wide ones flagged and costed as the light body */
     auto append = [&lists](const std::vector<int> &l, int ctas, int rcap) {
@@ -551,13 +591,13 @@ static int replan(skb_engine *e, cudaStream_t st) {
     if (e->n_wide_rows > 0) {
       std::vector<int> l; int ctas = 0, rcap = 0;
       for (int r = 0; r < nrows; r++) items[r] = row_wide[r] ? std::make_pair(5, r | SKB_ROW_WIDE) : std::make_pair(row_cost[r], r);
-      deal(items, e->n_sm, l, &ctas, &rcap);
+      deal(items, e->n_sm, l, &ctas, &rcap, affine);
       if (ctas != e->free_ctas || rcap != e->rows_cap) return fail(e, SKB_ERR_STATE, "planner: pass A list shape");
       e->list_a_wide = append(l, ctas, rcap);
       /* pass C: rows with a filter, the biquad / gain / mix part */
       items.clear();
       for (int r = 0; r < nrows; r++) if (row_wide[r] && row_filt[r]) items.push_back(std::make_pair(16, r));
-      if (!items.empty()) { deal(items, e->n_sm, l, &ctas, &rcap); e->list_c = append(l, ctas, rcap); }
+      if (!items.empty()) { deal(items, e->n_sm, l, &ctas, &rcap, nullptr); e->list_c = append(l, ctas, rcap); }
       /* pass B, per number of windows W of a launch: floor(#SM / W) CTAs per window */
       items.clear();
       for (int r = 0; r < nrows; r++)
@@ -565,7 +605,7 @@ static int replan(skb_engine *e, cudaStream_t st) {
       const int wmax = (e->cfg.max_frames + SKB_ENV_WIN - 1) / SKB_ENV_WIN;
       e->list_b.assign((size_t)wmax + 1, skb_engine::RowList());
       for (int W = SKB_WIDE_MIN_WIN; W <= wmax && W <= e->n_sm; W++) {
-        deal(items, std::max(1, e->n_sm / W), l, &ctas, &rcap);
+        deal(items, std::max(1, e->n_sm / W), l, &ctas, &rcap, nullptr);
         e->list_b[W] = append(l, ctas, rcap);
       }
       e->snap_nwin = wmax;

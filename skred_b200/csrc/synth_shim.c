@@ -125,6 +125,7 @@ static skb_engine *engine(void) {
   if ((s = getenv("SKB_FORCE_GENERIC")) && atoi(s)) cfg.flags |= SKB_CFG_FORCE_GENERIC;
   if ((s = getenv("SKB_NO_BATCH")) && atoi(s)) cfg.flags |= SKB_CFG_NO_BATCH;
   if ((s = getenv("SKB_WIDE")) && atoi(s)) cfg.flags |= SKB_CFG_WIDE;
+  if ((s = getenv("SKB_NO_AFFINE")) && atoi(s)) cfg.flags |= SKB_CFG_NO_AFFINE;
   int r = skb_create(&g_engine, &cfg);
   if (r != SKB_OK || !g_engine) {
     fprintf(stderr, "skred_b200: FATAL: cannot create %s engine (error %d); there is no CPU fallback\n",
