@@ -328,11 +328,16 @@ def own_arm(a):
     barrier()
     eng.skb_sync(sk.engine, sp)
     s_b = sk.stats()
+    tm = (C.c_double * 4)()
+    sk.lib.skb_shim_timing.argtypes = [C.c_void_p, C.c_int]
+    sk.lib.skb_shim_timing(tm, 1)
     t0 = time.perf_counter()
     for _ in range(a.steps):
         step_e2e()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    sk.lib.skb_shim_timing(tm, 0)
+    host_ms = [1e3 * x / a.steps for x in tm]
     eng.skb_sync(sk.engine, sp)
     s_a = sk.stats()
     clk = clocks.stop() if rank == 0 else None
@@ -397,7 +402,9 @@ def own_arm(a):
                 "warp_instructions_per_launch": ncu["warp_instructions"],
                 "note": "instruction count from the committed ncu capture of this command (profiles/r01_ncu_counters.json), duration measured live"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_s / a.steps * 1e3, "api": "synth(buffer, NULL, %d, 2, NULL)" % F},
+                    "ms_per_step": e2e_s / a.steps * 1e3, "api": "synth(buffer, NULL, %d, 2, NULL)" % F,
+                    "host_ms_per_step": None if world > 1 else {"flush_and_traces": host_ms[0], "queue_segments": host_ms[1],
+                                                                "fire_events": host_ms[2], "finish_launch_kernels_d2h_sync": host_ms[3]}},
             "gpu_launches": launches,
             "clocks": clk,
             "block_latency_ms_p50": None,

@@ -70,6 +70,7 @@ struct skb_engine {
   /* time-split ("wide") launches: free_kernel.cuh, passes A / B / C */
   struct RowList { int off = 0, ctas = 0, rows_cap = 0; };   /* rows at d_lists + off: [ctas][rows_cap] */
   RowList list_a_wide, list_c;
+  std::vector<int> cta_of_row, cta_of_row_wide;   /* pass-A CTA of every free row (the in-kernel ops are bucketed by it) */
   std::vector<RowList> list_b;       /* indexed by the number of windows of the launch */
   int *d_lists = nullptr; size_t lists_cap = 0;
   int n_wide_rows = 0, n_xrows = 0, snap_nwin = 0;
@@ -579,6 +580,15 @@ static int replan(skb_engine *e, cudaStream_t st) {
     std::vector<std::pair<int, int>> items((size_t)nrows);
     for (int r = 0; r < nrows; r++) items[r] = std::make_pair(row_cost[r], r);
     deal(items, e->n_sm, ctarows, &e->free_ctas, &e->rows_cap, affine);
+    auto invert = [nrows](const std::vector<int> &l, int ctas, int rcap, std::vector<int> &cta_of) {
+      cta_of.assign((size_t)std::max(nrows, 1), 0);
+      for (int c = 0; c < ctas; c++)
+        for (int k = 0; k < rcap; k++) {
+          const int rr = l[(size_t)c * rcap + k];
+          if (rr >= 0) cta_of[rr & ~SKB_ROW_WIDE] = c;
+        }
+    };
+    invert(ctarows, e->free_ctas, e->rows_cap, e->cta_of_row);
     e->free_groups = e->free_ctas * (e->rows_cap / SKB_CTA_WARPS);
     /* pass A of a time-split launch: the same rows, the wide ones flagged and costed as the light body */
     auto append = [&lists](const std::vector<int> &l, int ctas, int rcap) {
@@ -594,6 +604,7 @@ static int replan(skb_engine *e, cudaStream_t st) {
       deal(items, e->n_sm, l, &ctas, &rcap, affine);
       if (ctas != e->free_ctas || rcap != e->rows_cap) return fail(e, SKB_ERR_STATE, "planner: pass A list shape");
       e->list_a_wide = append(l, ctas, rcap);
+      invert(l, ctas, rcap, e->cta_of_row_wide);
       /* pass C: rows with a filter, the biquad / gain / mix part */
       items.clear();
       for (int r = 0; r < nrows; r++) if (row_wide[r] && row_filt[r]) items.push_back(std::make_pair(16, r));
@@ -826,16 +837,38 @@ static int batch_launch(skb_engine *e) {
   const int nwin = (int)e->batch.win_frames.size();
   const size_t nops = e->batch.ops.size();
   e->batch.win_ob.push_back((int)nops);                       /* CSR sentinel */
-  for (int w = 0; w < nwin; w++)                              /* per boundary: by slot, queue order within a voice */
+  /* time-split launch?  Needs enough windows to split, eligible rows, and no modulation bins */
+  const bool wide = e->n_wide_rows > 0 && nwin >= SKB_WIDE_MIN_WIN && nwin < (int)e->list_b.size() &&
+                    e->list_b[nwin].ctas > 0 && e->bins.empty() && (e->cfg.flags & SKB_CFG_WIDE) && !e->tap_on;
+  /* per boundary: by (CTA that renders the voice, slot), queue order within a voice; the kernel gets one CSR
+   * row per (boundary, CTA), so a CTA touches only its own ops — and most boundaries hold none for it */
+  const std::vector<int> &cta_of = wide ? e->cta_of_row_wide : e->cta_of_row;
+  const int ncta = std::max(e->free_ctas, 1);
+  const int n_free_pad = e->n_free_pad;
+  auto cta_of_slot = [&cta_of, n_free_pad](int slot) { return (slot >= 0 && slot < n_free_pad) ? cta_of[(size_t)(slot >> 5)] : 0; };
+  for (size_t i = 0; i < nops; i++) e->batch.ops[i]._pad = cta_of_slot(e->batch.ops[i].voice);   /* sort key; the kernel ignores it */
+  for (int w = 0; w < nwin; w++)
     std::stable_sort(e->batch.ops.begin() + e->batch.win_ob[w], e->batch.ops.begin() + e->batch.win_ob[w + 1],
-                     [](const skb_op &a, const skb_op &b) { return a.voice < b.voice; });
+                     [](const skb_op &a, const skb_op &b) { return a._pad != b._pad ? a._pad < b._pad : a.voice < b.voice; });
   cudaError_t r;
   if (wait_staging(e)) return e->err;
-  const size_t nwi = (size_t)2 * nwin + 1;
+  const size_t nwi = (size_t)nwin + (size_t)nwin * (ncta + 1);
   if ((r = grow_pin(&e->h_win, &e->h_win_cap, nwi)) != cudaSuccess || (r = grow_dev(&e->d_win, &e->win_cap, nwi)) != cudaSuccess)
     return fail(e, SKB_ERR_CUDA, "window list alloc", cudaGetErrorString(r));
   memcpy(e->h_win, e->batch.win_frames.data(), (size_t)nwin * sizeof(int));
-  memcpy(e->h_win + nwin, e->batch.win_ob.data(), (size_t)(nwin + 1) * sizeof(int));
+  {
+    int *csr = e->h_win + nwin;                               /* [nwin][ncta + 1] */
+    for (int w = 0; w < nwin; w++) {
+      int *row = csr + (size_t)w * (ncta + 1);
+      int i = e->batch.win_ob[w];
+      const int end = e->batch.win_ob[w + 1];
+      for (int c = 0; c <= ncta; c++) {
+        row[c] = i;
+        while (c < ncta && i < end && e->batch.ops[i]._pad == c) i++;
+      }
+      row[ncta] = end;
+    }
+  }
   CK(cudaMemcpyAsync(e->d_win, e->h_win, nwi * sizeof(int), cudaMemcpyHostToDevice, st));
   const unsigned *d_wake = nullptr;
   if (nops) {
@@ -854,9 +887,6 @@ static int batch_launch(skb_engine *e) {
   if (e->any_noise)
     CK(cudaMemcpyAsync(e->d_noise, e->h_noise, (size_t)nframes * sizeof(float), cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(e->ev_h2d, st));
-  /* time-split launch?  Needs enough windows to split, eligible rows, and no modulation bins */
-  const bool wide = e->n_wide_rows > 0 && nwin >= SKB_WIDE_MIN_WIN && nwin < (int)e->list_b.size() &&
-                    e->list_b[nwin].ctas > 0 && e->bins.empty() && (e->cfg.flags & SKB_CFG_WIDE) && !e->tap_on;
   const skb_engine::RowList lb = wide ? e->list_b[nwin] : skb_engine::RowList();
   const int groups_b = wide ? lb.ctas * (lb.rows_cap / SKB_CTA_WARPS) : 0;
   const int groups_c = (wide && e->list_c.ctas > 0) ? e->list_c.ctas * (e->list_c.rows_cap / SKB_CTA_WARPS) : 0;

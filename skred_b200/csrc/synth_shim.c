@@ -1056,6 +1056,14 @@ static int next_firing_boundary(int done, int num_frames, uint64_t start_count) 
   return num_frames + 1;
 }
 
+/* host-side time of synth(), seconds, accumulated: [0] flush + trace stepping, [1] skb_render_mix (queueing),
+ * [2] firing the due events (setters -> ops), [3] skb_finish (launch, kernels, D2H, sync) + tap readback */
+static double g_shim_time[4];
+static double shim_now(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec; }
+void skb_shim_timing(double *out4, int reset) {
+  for (int i = 0; i < 4; i++) { if (out4) out4[i] = g_shim_time[i]; if (reset) g_shim_time[i] = 0.0; }
+}
+
 void synth(float *buffer, float *input, int num_frames, int num_channels, void *user) {
   (void)input;
   /* `user`: the per-voice tap one_skred_frame[frame][voice][L,R], latched on the FIRST call only like the
@@ -1088,26 +1096,32 @@ void synth(float *buffer, float *input, int num_frames, int num_channels, void *
     while (done < chunk1) {
       /* render up to the next boundary at which a queued event fires (everything in between
        * is event-free, so one long launch equals many callbacks) */
+      const double t_a = shim_now();
       int end = next_firing_boundary(done, num_frames, start_count);
       const int fires = end <= chunk1;
       if (!fires) end = chunk1;
       if (skb_shim_flush() != SKB_OK) shim_die("flush");
       const int n = end - done;
       step_traces(n, 1);
+      const double t_b = shim_now();
       if (skb_render_mix(g_engine, n, synth_sample_count, g_noise, d_mix + (size_t)(done - chunk0) * 2, NULL) != SKB_OK)
         shim_die("skb_render_mix");
+      const double t_c = shim_now();
       synth_sample_count += (uint64_t)n;
       if (fires && n > 0) {
         const int sub = (end % EB) ? (end % EB) : EB;     /* length of the sub-block that just ended */
         fire_due(sub);
       }
       done = end;
+      g_shim_time[0] += t_b - t_a; g_shim_time[1] += t_c - t_b; g_shim_time[2] += shim_now() - t_c;
     }
+    const double t_f = shim_now();
     if (skb_finish(g_engine, d_mix, chunk1 - chunk0, g_gain, buffer + (size_t)chunk0 * num_channels, num_channels, NULL) != SKB_OK)
       shim_die("skb_finish");
     if (tap_user && skb_read_tap(g_engine, 0, chunk1 - chunk0, tap_user + (size_t)chunk0 * VOICE_MAX * 2) != SKB_OK)
       shim_die("skb_read_tap");                    /* synth.c:533-611 */
     g_gain_fill = 0;
+    g_shim_time[3] += shim_now() - t_f;
   }
   clock_gettime(CLOCK_MONOTONIC, &g_bench[slot].b);
   g_bench[slot].state = 2;
