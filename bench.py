@@ -338,6 +338,7 @@ def own_arm(a):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     sk.lib.skb_shim_timing(tm, 0)
     host_ms = [1e3 * x / a.steps for x in tm]
+    eng_us = [(x - y) / a.steps for x, y in zip(sk.stats().host_us, s_b.host_us)]
     eng.skb_sync(sk.engine, sp)
     s_a = sk.stats()
     clk = clocks.stop() if rank == 0 else None
@@ -404,7 +405,9 @@ def own_arm(a):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s / a.steps * 1e3, "api": "synth(buffer, NULL, %d, 2, NULL)" % F,
                     "host_ms_per_step": None if world > 1 else {"flush_and_traces": host_ms[0], "queue_segments": host_ms[1],
-                                                                "fire_events": host_ms[2], "finish_launch_kernels_d2h_sync": host_ms[3]}},
+                                                                "fire_events": host_ms[2], "finish_launch_kernels_d2h_sync": host_ms[3],
+                                                                "of_which_launch_host": eng_us[0] * 1e-3, "finish_enqueue": eng_us[1] * 1e-3,
+                                                                "stream_wait": eng_us[2] * 1e-3}},
             "gpu_launches": launches,
             "clocks": clk,
             "block_latency_ms_p50": None,

@@ -263,6 +263,9 @@ typedef struct skb_stats {
   uint64_t wide_errors;       /* rows a time-split pass had to drop (must stay 0) */
   float    last_wide_ms[3];   /* device time of passes A, B, C (+ row reduce) of the last time-split launch */
   int32_t  _pad2;
+  double   host_us[4];        /* diagnostics, host microseconds accumulated: [0] launching a batch (sorting its ops, staging,
+                                 H2D, kernel launches), [1] queueing skb_finish (wait for staging, gain H2D, k_finish, D2H),
+                                 [2] waiting for the stream in skb_finish, [3] unused */
 } skb_stats;
 int  skb_get_stats(skb_engine *e, skb_stats *out);
 

@@ -21,6 +21,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <queue>
@@ -137,6 +138,8 @@ struct skb_engine {
 };
 
 const char *skb_backend_name(void) { return "cuda-sm100a"; }
+
+static double host_now_us() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return 1e6 * (double)t.tv_sec + 1e-3 * (double)t.tv_nsec; }
 
 static int batch_launch(skb_engine *e);
 
@@ -831,6 +834,7 @@ int skb_owns_voice(skb_engine *e, int voice) {
 static int batch_launch(skb_engine *e) {
   if (!e->batch.open) return e->err;
   e->batch.open = false;
+  const double t_bl0 = host_now_us();
   const int nframes = e->batch.frames;
   if (nframes == 0) return e->err;
   cudaStream_t st = e->batch.st;
@@ -972,6 +976,7 @@ static int batch_launch(skb_engine *e) {
     CK(cudaMemsetAsync(e->batch.mix, 0, (size_t)nframes * sizeof(float2), st));
   }
   CK(cudaEventRecord(e->ev_t1, st));
+  e->stats.host_us[0] += host_now_us() - t_bl0;
   e->timing_pending = true;
   CK(cudaGetLastError());
   e->batch.frames = 0;
@@ -1056,6 +1061,7 @@ int skb_finish(skb_engine *e, const float *d_mix, int nframes, const float *gain
   cudaSetDevice(e->cfg.device);
   cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
   if (batch_launch(e)) return e->err;
+  const double t_f0 = host_now_us();
   if (use_stream(e, st)) return e->err;
   if (wait_staging(e)) return e->err;
   memcpy(e->h_gain, gain, (size_t)nframes * sizeof(float));
@@ -1065,7 +1071,10 @@ int skb_finish(skb_engine *e, const float *d_mix, int nframes, const float *gain
   e->stats.kernel_launches++;
   CK(cudaMemcpyAsync(e->h_out, e->d_out, (size_t)nframes * sizeof(float2), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(e->h_counters, e->d_counters, SKB_N_COUNTERS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  const double t_f1 = host_now_us();
   CK(cudaStreamSynchronize(st));
+  const double t_f2 = host_now_us();
+  e->stats.host_us[1] += t_f1 - t_f0; e->stats.host_us[2] += t_f2 - t_f1;
   e->stats.active_voice_frames = e->h_counters[0] + e->h_counters[1];
   for (int i = 0; i < 8; i++) e->stats.class_rows[i] = e->h_counters[2 + i];
   for (int i = 0; i < 8; i++) e->stats.phase_cycles[i] = e->h_counters[10 + i];
