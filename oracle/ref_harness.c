@@ -52,12 +52,66 @@ void util_set_thread_name(char *s) { (void)s; }
 char *udp_info(void) { return ""; }
 int udp_port = 0;
 
-/* WAV loading is outside the hot path; patches that need
- * `:w` are not used as parity inputs. */
+/* WAV loading, `:wN,slot[,ch]` (wire.c:406-441 -> mw_get, miniwav.c:103-147, which decodes through
+ * miniaudio).  miniaudio (95 k lines) is not compiled into the harness; this is OUR reader for what it would
+ * return for the files the reference ships — RIFF/WAVE integer PCM 16-bit, decoded to interleaved float32 with
+ * miniaudio's scaling x * 2^-15 (miniaudio.h:45560) — followed by mw_get's own channel handling restated as
+ * it is written, quirks included: with ch == -1 (the default of `:w`) nothing is stored, so the table is the
+ * first `frames` floats of the INTERLEAVED data (miniwav.c:126-137); ch > channels reads one past the frame.
+ * The same glue serves the compiled reference and the drop-in builds, so it cancels in the parity tests. */
+static uint32_t rd_u32(const unsigned char *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+static uint32_t rd_u16(const unsigned char *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
 float *mw_get(char *name, int *frames_out, wav_t *w, int ch) {
-  (void)name; (void)w; (void)ch;
   if (frames_out) *frames_out = 0;
-  return NULL;
+  FILE *f = fopen(name, "rb");
+  if (!f) return NULL;
+  fseek(f, 0, SEEK_END);
+  long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  unsigned char *b = (unsigned char *)malloc(sz > 0 ? (size_t)sz : 1);
+  if (sz < 44 || fread(b, 1, (size_t)sz, f) != (size_t)sz) { fclose(f); free(b); return NULL; }
+  fclose(f);
+  if (memcmp(b, "RIFF", 4) || memcmp(b + 8, "WAVE", 4)) { free(b); return NULL; }
+  int channels = 0, rate = 0, bits = 0, fmt = 0;
+  const unsigned char *data = NULL;
+  uint32_t data_len = 0;
+  for (long at = 12; at + 8 <= sz;) {
+    const uint32_t len = rd_u32(b + at + 4);
+    if (!memcmp(b + at, "fmt ", 4) && len >= 16) {
+      fmt = (int)rd_u16(b + at + 8); channels = (int)rd_u16(b + at + 10); rate = (int)rd_u32(b + at + 12); bits = (int)rd_u16(b + at + 22);
+    } else if (!memcmp(b + at, "data", 4)) {
+      data = b + at + 8;
+      data_len = (at + 8 + (long)len <= sz) ? len : (uint32_t)(sz - at - 8);
+      break;
+    }
+    at += 8 + (long)len + (len & 1);
+  }
+  if (!data || fmt != 1 || bits != 16 || channels < 1) { free(b); return NULL; }
+  const long frameCount = (long)(data_len / 2) / channels;
+  float *pSamples = (float *)malloc((size_t)(frameCount * channels + 1) * sizeof(float));
+  for (long i = 0; i < frameCount * channels; i++) {
+    const int16_t v = (int16_t)rd_u16(data + 2 * i);
+    pSamples[i] = (float)v * 0.000030517578125f;
+  }
+  pSamples[frameCount * channels] = 0.0f;
+  free(b);
+  /* miniwav.c:126-137 */
+  int j = 0;
+  if (ch > channels) ch = channels;
+  for (long i = 0; i < frameCount * channels; i += channels) {
+    if (ch == -1) {
+      float a = 0;
+      for (int k = 0; k < ch; k++) a += pSamples[i + k];
+      a /= (float)ch;
+    } else {
+      pSamples[j] = pSamples[i + ch];
+    }
+    j++;
+  }
+  w->SamplesRate = rate;
+  w->Channels = channels;
+  *frames_out = (int)frameCount;
+  return pSamples;
 }
 float *mw_free(float *f) { free(f); return NULL; }
 

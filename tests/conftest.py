@@ -26,6 +26,12 @@ def golden_patches():
 
 
 @pytest.fixture(scope="session")
+def golden_wav_patches():
+    import numpy as np
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "wav_patches.npz")))
+
+
+@pytest.fixture(scope="session")
 def golden_synth():
     import numpy as np
     return dict(np.load(os.path.join(ROOT, "tests", "golden", "synthetic.npz")))

@@ -12,6 +12,8 @@ Writes
                                  voice_phase / voice_finished traces (bit-exact targets)
   tests/golden/synthetic.npz     reference renders of the per-feature synthetic sets in
                                  tests/cases.py
+  tests/golden/wav_patches.npz   four shipped patches that load user samples (`:wN,slot`), their wav files
+                                 (bytes) and the reference render of 16 callbacks
 """
 import os
 import re
@@ -27,6 +29,8 @@ REF = os.environ.get("SKRED_REF", "/root/reference")
 
 GOLD_FRAMES = 8 * 512
 PATCHES = [0, 1, 3, 5, 7, 8, 15, 16, 17, 21, 23, 26, 29, 30, 31, 41, 42, 64, 71, 73]
+# patches that load user samples with `:wN,slot` (wire.c:406-441): the wav files they name travel as fixtures
+WAV_PATCHES = {13: [13, 16], 36: [3], 38: [17, 9], 44: [19]}
 
 
 def parse_tables(path, ctype):
@@ -86,6 +90,28 @@ def main():
         d["p%d_finished" % n] = fin
         print("patch %d: peak %.5f" % (n, np.abs(out).max()))
     np.savez_compressed(os.path.join(HERE, "patches.npz"), **d)
+    # user-sample patches: rendered with the cwd at the reference tree (wave_load opens "N.wav"); the wav bytes
+    # are stored next to the render so that the tests can write them into a scratch directory
+    d = {}
+    cwd = os.getcwd()
+    for n, wavs in WAV_PATCHES.items():
+        text = open(os.path.join(REF, "%d.sk" % n), "rb").read().decode("latin-1")
+        s = RefSkred(64)
+        os.chdir(REF)
+        try:
+            s.load_lines(text.splitlines())
+        finally:
+            os.chdir(cwd)
+        out, ph, fin = trace_render(s, 2 * GOLD_FRAMES)
+        d["p%d_text" % n] = np.array(text)
+        d["p%d_out" % n] = out
+        d["p%d_phase" % n] = ph
+        d["p%d_finished" % n] = fin
+        d["p%d_wavs" % n] = np.array(wavs, dtype=np.int32)
+        for wn in wavs:
+            d["wav%d" % wn] = np.frombuffer(open(os.path.join(REF, "%d.wav" % wn), "rb").read(), dtype=np.uint8)
+        print("wav patch %d: peak %.5f" % (n, np.abs(out).max()))
+    np.savez_compressed(os.path.join(HERE, "wav_patches.npz"), **d)
     d = {}
     for name, fn in cases.SYNTHETIC.items():
         wl = fn(luts)

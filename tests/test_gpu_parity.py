@@ -11,7 +11,7 @@ import pytest
 
 import cases
 from oracle import oracle as O
-from tests_util import PATCH_IDS, patch_lines, trace_render, assert_state_equal, FULL_SCALE_TOL
+from tests_util import PATCH_IDS, WAV_PATCH_IDS, load_wav_patch, patch_lines, trace_render, assert_state_equal, FULL_SCALE_TOL
 
 pytestmark = pytest.mark.gpu
 
@@ -363,3 +363,17 @@ def test_voice_tap_matches_reference(which, luts, golden_patches):
         assert maxdiff(oa2, ob2) <= FULL_SCALE_TOL
         assert np.array_equal(ta2.view(np.uint32), tb2.view(np.uint32))
     assert float(np.abs(ta).max()) > 0.0
+
+
+@pytest.mark.parametrize("n", WAV_PATCH_IDS)
+def test_wav_patch_vs_golden(n, golden_wav_patches, tmp_path):
+    """Shipped patches that play user samples loaded with `:wN,slot` (wire.c:406-441): one-shot
+    tables of 10-35 k samples at their own rate, re-triggered by the sequencer, FM / pan-mod / S&H on top.
+    Against the reference render: mix within the budget, phase and finished traces bit for bit."""
+    s = O.DropinCuda(64)
+    load_wav_patch(s, golden_wav_patches, n, tmp_path)
+    gold = golden_wav_patches["p%d_out" % n]
+    out, ph, fin = trace_render(s, gold.shape[0])
+    assert maxdiff(out, gold) <= FULL_SCALE_TOL
+    assert np.array_equal(ph.view(np.uint32), golden_wav_patches["p%d_phase" % n].view(np.uint32)), "phase trace"
+    assert np.array_equal(fin, golden_wav_patches["p%d_finished" % n]), "finished trace"

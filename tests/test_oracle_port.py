@@ -6,7 +6,7 @@ import pytest
 
 import cases
 from oracle import oracle as O
-from tests_util import PATCH_IDS, patch_lines, trace_render, assert_state_equal
+from tests_util import PATCH_IDS, WAV_PATCH_IDS, load_wav_patch, patch_lines, trace_render, assert_state_equal
 
 needs_ref = pytest.mark.skipif(not O.have_ref(64), reason="compiled reference (oracle/_ref) not present")
 
@@ -109,3 +109,27 @@ def test_port_tap_matches_reference(n, golden_patches):
     assert np.array_equal(oa.view(np.uint32), ob.view(np.uint32))
     assert np.array_equal(ta.view(np.uint32), tb.view(np.uint32))
     assert float(np.abs(ta).max()) > 0.0
+
+
+@pytest.mark.parametrize("n", WAV_PATCH_IDS)
+def test_port_matches_golden_wav_patch(n, golden_wav_patches, tmp_path):
+    """Shipped patches that load user samples (`:wN,slot`, wire.c:406-441): the table arrives through
+    wave_table_data[] / wave_size[] / wave_one_shot[] ... exactly as wire.c leaves them, the shim uploads it."""
+    s = O.PortSkred(64)
+    load_wav_patch(s, golden_wav_patches, n, tmp_path)
+    gold = golden_wav_patches["p%d_out" % n]
+    out, ph, fin = trace_render(s, gold.shape[0])
+    assert np.array_equal(out.view(np.uint32), gold.view(np.uint32))
+    assert np.array_equal(ph.view(np.uint32), golden_wav_patches["p%d_phase" % n].view(np.uint32))
+    assert np.array_equal(fin, golden_wav_patches["p%d_finished" % n])
+    assert float(np.abs(gold).max()) > 0.0
+
+
+@needs_ref
+@pytest.mark.parametrize("n", WAV_PATCH_IDS)
+def test_reference_matches_golden_wav_patch(n, golden_wav_patches, tmp_path):
+    s = O.RefSkred(64)
+    load_wav_patch(s, golden_wav_patches, n, tmp_path)
+    gold = golden_wav_patches["p%d_out" % n]
+    out, ph, fin = trace_render(s, gold.shape[0])
+    assert np.array_equal(out.view(np.uint32), gold.view(np.uint32))

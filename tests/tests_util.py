@@ -4,6 +4,24 @@ PATCH_IDS = [0, 1, 3, 5, 7, 8, 15, 16, 17, 21, 23, 26, 29, 30, 31, 41, 42, 64, 7
 FULL_SCALE_TOL = 1e-5      # north_star: within 1e-5 of full scale (1.0) per sample on float paths
 
 
+WAV_PATCH_IDS = [13, 36, 38, 44]     # shipped patches that load user samples with `:wN,slot` (wire.c:406-441)
+
+
+def load_wav_patch(s, golden_wav, n, tmpdir):
+    """Feed a user-sample patch to `s` with the wav files it names (fixtures) in the working directory,
+    which is where wave_load looks for "N.wav" (wire.c:409)."""
+    import os
+    for wn in golden_wav["p%d_wavs" % n]:
+        with open(os.path.join(str(tmpdir), "%d.wav" % int(wn)), "wb") as f:
+            f.write(golden_wav["wav%d" % int(wn)].tobytes())
+    cwd = os.getcwd()
+    os.chdir(str(tmpdir))
+    try:
+        s.load_lines(str(golden_wav["p%d_text" % n]).splitlines())
+    finally:
+        os.chdir(cwd)
+
+
 def patch_lines(golden, n):
     return str(golden["p%d_text" % n]).splitlines()
 
