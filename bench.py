@@ -257,10 +257,34 @@ def own_arm(a):
             sk.render_mix(LF, mix_ptr + b * 8, sp)
         sk.lib.skb_shim_flush_render()
 
+    # N > 1, device-resident loop: the NCCL reduce of step k runs on its own stream while the engine renders
+    # step k + 1 into the other mix buffer (a batch render has no reason to serialise them)
+    comm = torch.cuda.Stream() if world > 1 else None
+    d_mix2 = [d_mix, torch.zeros_like(d_mix)] if world > 1 else [d_mix]
+    rendered = [torch.cuda.Event() for _ in d_mix2]
+    reduced = [torch.cuda.Event() for _ in d_mix2]
+    step_no = [0]
+
     def step_device():
-        render_step()
+        if world == 1:
+            render_step()
+            return
+        k = step_no[0] % 2
+        step_no[0] += 1
+        stream.wait_event(reduced[k])                     # the reduce that last read this buffer is done
+        ptr = d_mix2[k].data_ptr()
+        for b in range(0, F, LF):
+            sk.render_mix(LF, ptr + b * 8, sp)
+        sk.lib.skb_shim_flush_render()
+        rendered[k].record(stream)
+        with torch.cuda.stream(comm):
+            comm.wait_event(rendered[k])
+            dist.reduce(d_mix2[k], dst=0, op=dist.ReduceOp.SUM)
+            reduced[k].record(comm)
+
+    def drain_device():
         if world > 1:
-            dist.reduce(d_mix, dst=0, op=dist.ReduceOp.SUM)
+            stream.wait_stream(comm)
 
     def step_e2e():
         if world == 1:
@@ -290,6 +314,7 @@ def own_arm(a):
     for _ in range(a.warmup):
         step_device()
         sk.lib.skb_shim_discard_gain()
+    drain_device()
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:
@@ -302,6 +327,7 @@ def own_arm(a):
     for _ in range(a.steps):
         step_device()
         sk.lib.skb_shim_discard_gain()
+    drain_device()
     e1.record(stream)
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
@@ -315,6 +341,7 @@ def own_arm(a):
         a_b = sk.stats().active_voice_frames
         step_device()
         sk.lib.skb_shim_discard_gain()
+        drain_device()
         eng.skb_sync(sk.engine, sp)
         st_k = sk.stats()
         kern_ms.append(st_k.last_render_ms)
@@ -386,7 +413,8 @@ def own_arm(a):
                        "active_fraction": act_dev / (V * F * a.steps),
                        "counting": "rendered voice-frames only: voices skipped by synth.c:531-542 (finished one-shots) do not count",
                        "value_counting_all_voice_slots": V * F * a.steps / (dev_ms * 1e-3),
-                       "parallelism": "voice-sharded x%d, NCCL reduce of stereo partials" % world if world > 1 else "1 GPU",
+                       "parallelism": ("voice-sharded x%d, NCCL reduce of stereo partials (value: the reduce of step k overlaps the render "
+                                       "of step k + 1 on a second stream; e2e: render -> reduce -> finish in order)" % world) if world > 1 else "1 GPU",
                        "launches": "the engine renders the %d callbacks of a step in one launch; events are applied in-kernel at the 512-frame boundaries" % (F // LF),
                        "l2": "state+params %.1f MB per launch, each word touched once per launch (no reuse to cache)" % (owned * 276 / 1e6)},
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,

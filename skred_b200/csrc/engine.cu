@@ -132,9 +132,12 @@ struct skb_engine {
     std::vector<int> wake_words;        /* ... and which words are non-zero */
     int tap_frame0 = 0;                 /* first frame of the batch in the tap buffer (= its offset in the caller's mix) */
   } batch;
-  int *d_win = nullptr, *h_win = nullptr; size_t win_cap = 0, h_win_cap = 0;
-  skb_op *d_bops = nullptr, *h_bops = nullptr; size_t bops_cap = 0, h_bops_cap = 0;
-  uint32_t *d_wake = nullptr, *h_wake = nullptr; size_t wake_cap = 0, h_wake_cap = 0;
+  /* per-launch staging block (window list, op CSR, ops, wake bits), double buffered, uploaded on copy_stream */
+  char *h_stage[2] = {nullptr, nullptr}, *d_stage[2] = {nullptr, nullptr};
+  size_t h_stage_cap[2] = {0, 0}, d_stage_cap[2] = {0, 0};
+  int stage_idx = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_stage_copied[2] = {nullptr, nullptr}, ev_stage_done[2] = {nullptr, nullptr};
 };
 
 const char *skb_backend_name(void) { return "cuda-sm100a"; }
@@ -199,7 +202,7 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
   e->cfg = *cfg;
   if (e->cfg.max_frames < 512) e->cfg.max_frames = 512;
   e->n = cfg->n_voices;
-  e->n_sm = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+  e->n_sm = (prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148) * SKB_CTAS_PER_SM;   /* = CTA slots of the GPU */
   memset(&e->stats, 0, sizeof(e->stats));
   const int n = e->n, mf = e->cfg.max_frames;
   e->cap = ((n + 31) / 32) * 32 + 64 + 32 * 8;        /* + class padding of the free range */
@@ -231,6 +234,11 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
             cudaMemset(e->d_tickets, 0, (size_t)(mf / SKB_RED_X + 1) * sizeof(unsigned int)) == cudaSuccess &&
             cudaMemset(e->d_counters, 0, SKB_N_COUNTERS * sizeof(unsigned long long)) == cudaSuccess &&
             cudaEventCreate(&e->ev_a) == cudaSuccess && cudaEventCreate(&e->ev_b) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_stage_copied[0], cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_stage_copied[1], cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_stage_done[0], cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_stage_done[1], cudaEventDisableTiming) == cudaSuccess &&
             cudaFuncSetAttribute(k_render_free, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)skb_free_smem_bytes()) == cudaSuccess &&
             cudaFuncSetAttribute(k_render_free_tap, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -269,12 +277,16 @@ void skb_destroy(skb_engine *e) {
   cudaFree(e->d_gain); cudaFree(e->d_noise); cudaFree(e->d_idx); cudaFree(e->d_recs);
   cudaFree(e->d_ops); cudaFree(e->d_runs); cudaFree(e->d_vsnap);
   cudaFree(e->d_envbuf); cudaFree(e->d_ctarows); cudaFree(e->d_ctaphase);
-  cudaFree(e->d_win); cudaFree(e->d_bops); cudaFree(e->d_wake);
+  for (int i = 0; i < 2; i++) {
+    cudaFree(e->d_stage[i]); cudaFreeHost(e->h_stage[i]);
+    if (e->ev_stage_copied[i]) cudaEventDestroy(e->ev_stage_copied[i]);
+    if (e->ev_stage_done[i]) cudaEventDestroy(e->ev_stage_done[i]);
+  }
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   cudaFree(e->d_lists); cudaFree(e->d_xrow); cudaFree(e->d_snap); cudaFree(e->d_xs);
   cudaFree(e->d_tap); cudaFree(e->d_vos); cudaFreeHost(e->h_tap);
   if (e->ev_a) cudaEventDestroy(e->ev_a);
   if (e->ev_b) cudaEventDestroy(e->ev_b);
-  cudaFreeHost(e->h_win); cudaFreeHost(e->h_bops); cudaFreeHost(e->h_wake);
   cudaFree(e->d_part2); cudaFree(e->d_tickets); cudaFree(e->d_counters);
   cudaFreeHost(e->h_counters);
   cudaFreeHost(e->h_gain); cudaFreeHost(e->h_noise); cudaFreeHost(e->h_out); cudaFreeHost(e->h_idx);
@@ -739,7 +751,8 @@ static int use_stream(skb_engine *e, cudaStream_t st) {
 
 /* Bring the device up to date with everything the host sent: plan, parameter
  * records, ordered ops. */
-static int sync_inputs(skb_engine *e, cudaStream_t st) {
+/* defer_ops: leave the queued ops for the kernel to apply at its first boundary when it can (no bins). */
+static int sync_inputs(skb_engine *e, cudaStream_t st, bool defer_ops = false) {
   if (e->err) return e->err;
   if (!e->planned) e->need_plan = true;
   if (!e->need_plan)
@@ -781,7 +794,7 @@ static int sync_inputs(skb_engine *e, cudaStream_t st) {
     }
     e->any_noise = e->noise_count > 0;
   }
-  if (!e->ops.empty()) {
+  if (!e->ops.empty() && !(defer_ops && e->bins.empty() && !(e->cfg.flags & SKB_CFG_NO_BATCH))) {
     /* keep per-voice order: stable sort by slot, then one run per slot */
     std::vector<skb_op> &ops = e->ops;
     size_t cnt = 0;
@@ -856,12 +869,26 @@ static int batch_launch(skb_engine *e) {
                      [](const skb_op &a, const skb_op &b) { return a._pad != b._pad ? a._pad < b._pad : a.voice < b.voice; });
   cudaError_t r;
   if (wait_staging(e)) return e->err;
+  /* ONE staging block per launch — [window frames | per-(boundary, CTA) CSR | ops | wake bits] — copied by one
+   * H2D on a COPY stream, double buffered: while launch k renders, the host stages and uploads launch k + 1,
+   * and the render stream only waits on an event that has long fired (three dependent copies on the render
+   * stream cost ~15-20 us of a 0.4 ms step). */
   const size_t nwi = (size_t)nwin + (size_t)nwin * (ncta + 1);
-  if ((r = grow_pin(&e->h_win, &e->h_win_cap, nwi)) != cudaSuccess || (r = grow_dev(&e->d_win, &e->win_cap, nwi)) != cudaSuccess)
-    return fail(e, SKB_ERR_CUDA, "window list alloc", cudaGetErrorString(r));
-  memcpy(e->h_win, e->batch.win_frames.data(), (size_t)nwin * sizeof(int));
+  const size_t nw = nops ? ((size_t)e->cap + 31) / 32 : 0;
+  const size_t off_ops = (nwi * sizeof(int) + 15) & ~(size_t)15;
+  const size_t off_wake = off_ops + nops * sizeof(skb_op);
+  const size_t stage_bytes = off_wake + nw * sizeof(uint32_t);
+  const int sb = e->stage_idx;
+  e->stage_idx ^= 1;
+  CK(cudaEventSynchronize(e->ev_stage_done[sb]));          /* the launch that last read this block is over (two launches ago) */
+  if ((r = grow_pin(&e->h_stage[sb], &e->h_stage_cap[sb], stage_bytes)) != cudaSuccess ||
+      (r = grow_dev(&e->d_stage[sb], &e->d_stage_cap[sb], stage_bytes)) != cudaSuccess)
+    return fail(e, SKB_ERR_CUDA, "launch staging alloc", cudaGetErrorString(r));
+  char *hs = e->h_stage[sb];
+  char *ds = e->d_stage[sb];
+  memcpy(hs, e->batch.win_frames.data(), (size_t)nwin * sizeof(int));
   {
-    int *csr = e->h_win + nwin;                               /* [nwin][ncta + 1] */
+    int *csr = (int *)hs + nwin;                              /* [nwin][ncta + 1] */
     for (int w = 0; w < nwin; w++) {
       int *row = csr + (size_t)w * (ncta + 1);
       int i = e->batch.win_ob[w];
@@ -873,21 +900,19 @@ static int batch_launch(skb_engine *e) {
       row[ncta] = end;
     }
   }
-  CK(cudaMemcpyAsync(e->d_win, e->h_win, nwi * sizeof(int), cudaMemcpyHostToDevice, st));
+  const int *d_winp = (const int *)ds;
+  const skb_op *d_bopsp = (const skb_op *)(ds + off_ops);
   const unsigned *d_wake = nullptr;
   if (nops) {
-    const size_t nw = ((size_t)e->cap + 31) / 32;
-    if ((r = grow_pin(&e->h_bops, &e->h_bops_cap, nops)) != cudaSuccess || (r = grow_dev(&e->d_bops, &e->bops_cap, nops)) != cudaSuccess ||
-        (r = grow_pin(&e->h_wake, &e->h_wake_cap, nw)) != cudaSuccess || (r = grow_dev(&e->d_wake, &e->wake_cap, nw)) != cudaSuccess)
-      return fail(e, SKB_ERR_CUDA, "batch op alloc", cudaGetErrorString(r));
-    memcpy(e->h_bops, e->batch.ops.data(), nops * sizeof(skb_op));
-    memcpy(e->h_wake, e->batch.wake.data(), nw * sizeof(uint32_t));
-    CK(cudaMemcpyAsync(e->d_bops, e->h_bops, nops * sizeof(skb_op), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(e->d_wake, e->h_wake, nw * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    d_wake = e->d_wake;
+    memcpy(hs + off_ops, e->batch.ops.data(), nops * sizeof(skb_op));
+    memcpy(hs + off_wake, e->batch.wake.data(), nw * sizeof(uint32_t));
+    d_wake = (const unsigned *)(ds + off_wake);
     for (size_t i = 0; i < e->batch.wake_words.size(); i++) e->batch.wake[e->batch.wake_words[i]] = 0u;
     e->batch.wake_words.clear();
   }
+  CK(cudaMemcpyAsync(ds, hs, stage_bytes, cudaMemcpyHostToDevice, e->copy_stream));
+  CK(cudaEventRecord(e->ev_stage_copied[sb], e->copy_stream));
+  CK(cudaStreamWaitEvent(st, e->ev_stage_copied[sb], 0));
   if (e->any_noise)
     CK(cudaMemcpyAsync(e->d_noise, e->h_noise, (size_t)nframes * sizeof(float), cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(e->ev_h2d, st));
@@ -920,8 +945,8 @@ static int batch_launch(skb_engine *e) {
     fa.cta_rowlist = wide ? e->d_lists + e->list_a_wide.off : e->d_ctarows; fa.rows_cap = e->rows_cap;
     fa.tables = e->d_tables; fa.noise = e->d_noise;
     fa.nframes = nframes; fa.ssc_before = (unsigned long long)e->batch.ssc0;
-    fa.win_frames = e->d_win; fa.win_ob = e->d_win + nwin; fa.nwin = nwin;
-    fa.bops = e->d_bops; fa.wake = d_wake;
+    fa.win_frames = d_winp; fa.win_ob = d_winp + nwin; fa.nwin = nwin;
+    fa.bops = d_bopsp; fa.wake = d_wake;
     fa.ctarows = e->d_partials; fa.row_stride = nframes;
     fa.envbuf = e->d_envbuf; fa.counters = e->d_counters; fa.cta_phase = e->d_ctaphase;
     fa.force_generic = (e->cfg.flags & SKB_CFG_FORCE_GENERIC) ? 1 : 0;
@@ -976,6 +1001,7 @@ static int batch_launch(skb_engine *e) {
     CK(cudaMemsetAsync(e->batch.mix, 0, (size_t)nframes * sizeof(float2), st));
   }
   CK(cudaEventRecord(e->ev_t1, st));
+  CK(cudaEventRecord(e->ev_stage_done[sb], st));
   e->stats.host_us[0] += host_now_us() - t_bl0;
   e->timing_pending = true;
   CK(cudaGetLastError());
@@ -1011,7 +1037,7 @@ int skb_render_mix(skb_engine *e, int nframes, uint64_t ssc_before, const float 
   if (!extend) {
     if (batch_launch(e)) return e->err;
     if (use_stream(e, st)) return e->err;
-    if (sync_inputs(e, st)) return e->err;        /* plan, parameter records, ops -> k_apply_ops */
+    if (sync_inputs(e, st, true)) return e->err;  /* plan, parameter records; ops -> k_apply_ops only if the kernel cannot take them */
     if (nframes == 0) return e->err;
     e->batch.open = true; e->batch.st = st; e->batch.mix = d_mix; e->batch.frames = 0; e->batch.ssc0 = ssc_before;
     e->batch.tap_frame0 = e->tap_cursor;
@@ -1027,7 +1053,7 @@ int skb_render_mix(skb_engine *e, int nframes, uint64_t ssc_before, const float 
   }
   /* this segment's windows; the queued ops belong to the boundary before its first window */
   e->batch.win_ob.push_back((int)e->batch.ops.size());
-  if (extend && !e->ops.empty()) {
+  if (!e->ops.empty()) {          /* (a new batch: the boundary before its first window) */
     for (size_t i = 0; i < e->ops.size(); i++) {
       skb_op op = e->ops[i];
       const int v = op.voice;
