@@ -9,7 +9,7 @@ config-2 / config-3 / config-4 recipe by v%3 (LUT + ADSR + pan, Korg + CZ +
 resonant biquad + ADSR, AMY one-shot PCM with pitch shift), amplitudes 40/V,
 one (re)trigger per voice per 10 s as timestamped events applied at 512-frame
 block boundaries.  One STEP = one batch of `--frames` frames
-(default 4096 = 8 reference callbacks) of all voices.
+(default 8192 = 16 reference callbacks, the engine's largest launch) of all voices.
 
   value   device-resident: params/state/tables/pending events live in HBM; K steps of
           skb_shim_render_mix (+ NCCL reduce of the stereo partial mixes for N > 1),
@@ -399,7 +399,9 @@ def own_arm(a):
     alive_pcm = max(0.0, alive_per_launch - 2.0 * owned / 3.0)
     flops_vs = (owned / 3.0 * 15.0 + owned / 3.0 * 32.0 + alive_pcm * 15.0) / max(alive_per_launch, 1.0)
     ach_flops = k_act * flops_vs / (k_ms * 1e-3)
-    ncu = load_ncu_counters() if (V == 65536 and F == 4096 and world == 1) else None
+    ncu = load_ncu_counters() if (V == 65536 and world == 1) else None
+    if ncu and ncu.get("frames", 4096) != F:
+        ncu = None
     traffic = float(ncu["dram_bytes_read"] + ncu["dram_bytes_write"]) if ncu else None
     issue_peak = N_SM * 4 * sm_mhz * 1e6                     # warp instructions per second: 4 schedulers per SM
 
@@ -481,7 +483,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--voices", type=int, default=65536)
-    ap.add_argument("--frames", type=int, default=4096, help="frames per step (multiple of 512)")
+    ap.add_argument("--frames", type=int, default=8192, help="frames per step (multiple of 512; <= 8192)")
     ap.add_argument("--launch-frames", type=int, default=512)
     ap.add_argument("--ref-frames", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true")

@@ -136,6 +136,7 @@ struct skb_engine {
   char *h_stage[2] = {nullptr, nullptr}, *d_stage[2] = {nullptr, nullptr};
   size_t h_stage_cap[2] = {0, 0}, d_stage_cap[2] = {0, 0};
   int stage_idx = 0;
+  std::vector<int> sort_cursor;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_stage_copied[2] = {nullptr, nullptr}, ev_stage_done[2] = {nullptr, nullptr};
 };
@@ -863,10 +864,7 @@ static int batch_launch(skb_engine *e) {
   const int ncta = std::max(e->free_ctas, 1);
   const int n_free_pad = e->n_free_pad;
   auto cta_of_slot = [&cta_of, n_free_pad](int slot) { return (slot >= 0 && slot < n_free_pad) ? cta_of[(size_t)(slot >> 5)] : 0; };
-  for (size_t i = 0; i < nops; i++) e->batch.ops[i]._pad = cta_of_slot(e->batch.ops[i].voice);   /* sort key; the kernel ignores it */
-  for (int w = 0; w < nwin; w++)
-    std::stable_sort(e->batch.ops.begin() + e->batch.win_ob[w], e->batch.ops.begin() + e->batch.win_ob[w + 1],
-                     [](const skb_op &a, const skb_op &b) { return a._pad != b._pad ? a._pad < b._pad : a.voice < b.voice; });
+  for (size_t i = 0; i < nops; i++) e->batch.ops[i]._pad = cta_of_slot(e->batch.ops[i].voice);   /* bucket key; the kernel ignores it */
   cudaError_t r;
   if (wait_staging(e)) return e->err;
   /* ONE staging block per launch — [window frames | per-(boundary, CTA) CSR | ops | wake bits] — copied by one
@@ -888,23 +886,36 @@ static int batch_launch(skb_engine *e) {
   char *ds = e->d_stage[sb];
   memcpy(hs, e->batch.win_frames.data(), (size_t)nwin * sizeof(int));
   {
+    /* counting sort of every boundary's ops by CTA straight into the staging block (stable: queue order within
+     * a voice survives), then by slot inside the few-op buckets; the bucket starts are the CSR rows */
     int *csr = (int *)hs + nwin;                              /* [nwin][ncta + 1] */
+    skb_op *outp = (skb_op *)(hs + off_ops);
+    e->sort_cursor.assign((size_t)ncta + 1, 0);
+    int *cur = e->sort_cursor.data();
     for (int w = 0; w < nwin; w++) {
       int *row = csr + (size_t)w * (ncta + 1);
-      int i = e->batch.win_ob[w];
-      const int end = e->batch.win_ob[w + 1];
-      for (int c = 0; c <= ncta; c++) {
-        row[c] = i;
-        while (c < ncta && i < end && e->batch.ops[i]._pad == c) i++;
+      const int b = e->batch.win_ob[w], en = e->batch.win_ob[w + 1];
+      for (int c = 0; c <= ncta; c++) cur[c] = 0;
+      for (int i = b; i < en; i++) cur[e->batch.ops[i]._pad]++;
+      int pos = b;
+      for (int c = 0; c < ncta; c++) { row[c] = pos; pos += cur[c]; cur[c] = row[c]; }
+      row[ncta] = en;
+      for (int i = b; i < en; i++) outp[cur[e->batch.ops[i]._pad]++] = e->batch.ops[i];
+      for (int c = 0; c < ncta; c++) {
+        const int s0 = row[c], s1 = row[c + 1];
+        for (int i = s0 + 1; i < s1; i++) {                   /* insertion sort by slot, stable */
+          const skb_op key = outp[i];
+          int j = i;
+          while (j > s0 && outp[j - 1].voice > key.voice) { outp[j] = outp[j - 1]; j--; }
+          outp[j] = key;
+        }
       }
-      row[ncta] = end;
     }
   }
   const int *d_winp = (const int *)ds;
   const skb_op *d_bopsp = (const skb_op *)(ds + off_ops);
   const unsigned *d_wake = nullptr;
   if (nops) {
-    memcpy(hs + off_ops, e->batch.ops.data(), nops * sizeof(skb_op));
     memcpy(hs + off_wake, e->batch.wake.data(), nw * sizeof(uint32_t));
     d_wake = (const unsigned *)(ds + off_wake);
     for (size_t i = 0; i < e->batch.wake_words.size(); i++) e->batch.wake[e->batch.wake_words[i]] = 0u;
