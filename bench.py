@@ -250,12 +250,17 @@ def own_arm(a):
     LF = a.launch_frames                     # frames per launch: events land on 512-frame boundaries
     mix_ptr = d_mix.data_ptr()
 
+    sk.lib.skb_shim_render_calls.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+
+    def render_calls(ptr):
+        # one callback-sized segment per skb_shim_render_mix, like a host's audio callback; the engine batches
+        # the calls of a step into one launch and applies the events at the 512-frame boundaries itself
+        r = sk.lib.skb_shim_render_calls(LF, F // LF, ptr, sp)
+        if r != 0:
+            raise RuntimeError("render failed %d" % r)
+
     def render_step():
-        # one callback-sized segment per call, like a host's audio callback; the engine batches the
-        # calls of a step into one launch and applies the events at the 512-frame boundaries itself
-        for b in range(0, F, LF):
-            sk.render_mix(LF, mix_ptr + b * 8, sp)
-        sk.lib.skb_shim_flush_render()
+        render_calls(mix_ptr)
 
     # N > 1, device-resident loop: the NCCL reduce of step k runs on its own stream while the engine renders
     # step k + 1 into the other mix buffer (a batch render has no reason to serialise them)
@@ -272,10 +277,7 @@ def own_arm(a):
         k = step_no[0] % 2
         step_no[0] += 1
         stream.wait_event(reduced[k])                     # the reduce that last read this buffer is done
-        ptr = d_mix2[k].data_ptr()
-        for b in range(0, F, LF):
-            sk.render_mix(LF, ptr + b * 8, sp)
-        sk.lib.skb_shim_flush_render()
+        render_calls(d_mix2[k].data_ptr())
         rendered[k].record(stream)
         with torch.cuda.stream(comm):
             comm.wait_event(rendered[k])

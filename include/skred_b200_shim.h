@@ -97,6 +97,10 @@ int  skb_shim_finish(const float *d_mix, int num_frames, float *out, int num_cha
  * master-volume trace accumulated by its skb_shim_render_mix calls. */
 void skb_shim_discard_gain(void);
 
+/* `ncalls` consecutive callbacks of `frames_per_call` frames rendered into d_mix back to back, then launched
+ * (skb_shim_render_mix x ncalls + skb_shim_flush_render). */
+int skb_shim_render_calls(int frames_per_call, int ncalls, float *d_mix, void *stream);
+
 /* Diagnostics: host-side seconds spent inside synth() since the last reset: [0] flush + master-volume / noise
  * trace stepping, [1] skb_render_mix (queueing the segments), [2] firing due events (setters -> device ops),
  * [3] skb_finish (launch, kernels, D2H, synchronisation) and the tap readback. */

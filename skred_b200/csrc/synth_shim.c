@@ -72,8 +72,11 @@ float volume_smoother_higher_smoothing = 0.3f;
 /* ======================================================================== */
 static skb_engine *g_engine = NULL;
 static int g_cfg_device = 0, g_cfg_rank = 0, g_cfg_world = 1, g_cfg_max_frames = 8192;
-static int g_early_flush_frames = 0;      /* $SKB_EARLY_FLUSH: frames after which synth() launches what it has queued; 0 = one launch per
-                                             chunk (measured: a second launch costs more than the overlap wins, 0.496 vs 0.502-0.529 ms) */
+static int g_early_flush_frames = 4096;   /* $SKB_EARLY_FLUSH: frames after which synth() launches what it has queued when at least
+                                             as many are still to come, so the GPU renders the first half of a long call while the
+                                             host fires and queues the events of the second (0 = one launch per chunk).  Measured:
+                                             synth(8192) 0.821 vs 0.848 ms; shorter halves lose (synth(4096) split at 2048: 0.529 vs
+                                             0.496 ms), a second launch costs ~45 us */
 static int g_scan_all = (VOICE_MAX <= 4096);
 
 static uint8_t g_dirty[VOICE_MAX];
@@ -1154,6 +1157,16 @@ int skb_shim_render_mix(int num_frames, float *d_mix, void *stream) {
   synth_sample_count += (uint64_t)num_frames;
   fire_due(num_frames);        /* seq()'s rule for this callback */
   return r;
+}
+
+/* `ncalls` consecutive callbacks of `frames_per_call` frames into d_mix (frames_per_call * ncalls * 2 floats),
+ * then launch: what a host loop over skb_shim_render_mix + skb_shim_flush_render does, in one call. */
+int skb_shim_render_calls(int frames_per_call, int ncalls, float *d_mix, void *stream) {
+  for (int k = 0; k < ncalls; k++) {
+    const int r = skb_shim_render_mix(frames_per_call, d_mix + (size_t)k * frames_per_call * 2, stream);
+    if (r != SKB_OK) return r;
+  }
+  return skb_flush(engine());
 }
 
 void skb_shim_discard_gain(void) { g_gain_fill = 0; }
