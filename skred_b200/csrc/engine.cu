@@ -203,7 +203,7 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
   e->cfg = *cfg;
   if (e->cfg.max_frames < 512) e->cfg.max_frames = 512;
   e->n = cfg->n_voices;
-  e->n_sm = (prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148) * SKB_CTAS_PER_SM;   /* = CTA slots of the GPU */
+  e->n_sm = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
   memset(&e->stats, 0, sizeof(e->stats));
   const int n = e->n, mf = e->cfg.max_frames;
   e->cap = ((n + 31) / 32) * 32 + 64 + 32 * 8;        /* + class padding of the free range */
