@@ -394,8 +394,10 @@ def own_arm(a):
     clk = clocks.stop() if rank == 0 else None
     ops = int(s_a.ops_applied - s_b.ops_applied)
     par = int(s_a.params_uploaded - s_b.params_uploaded)
-    h2d = (ops * 32 + par * 132 + a.steps * F * 4) / a.steps
-    d2h = F * 8
+    # counted by the engine from the copies it issues (skb_stats.h2d_bytes / d2h_bytes): parameter records, the
+    # per-launch staging block (window list, op lists, wake bits), gain trace; stereo block + counters back
+    h2d = (s_a.h2d_bytes - s_b.h2d_bytes) / a.steps
+    d2h = (s_a.d2h_bytes - s_b.d2h_bytes) / a.steps
 
     def sum_over_ranks(x):
         if world == 1:
@@ -470,6 +472,7 @@ def own_arm(a):
         }
         if world == 1 and not a.no_latency:
             line["block_latency_ms_p50"] = block_latency(sk, a.latency_blocks)
+            line["block_latency_ms_p50_64_voices"] = block_latency_small(local, a.latency_blocks)
         if world == 1 and not a.no_cpu:
             line["cpu_baseline"] = cpu_baseline(V)
         print(json.dumps(line))
@@ -488,6 +491,21 @@ def block_latency(sk, nblocks):
         sk.lib.synth(out.ctypes.data, None, 512, 2, None)
         ts.append(time.perf_counter() - t0)
     return float(np.median(ts) * 1e3)
+
+
+def block_latency_small(device, nblocks):
+    """The same for skred as shipped: VOICE_MAX = 64 (BASELINE configs[1]: LUT oscillators + ADSR + pan), one
+    512-frame callback per call — what the audio thread of a real-time host would see."""
+    from skred_b200 import Skred
+    from skred_b200.host import shim_lib_path
+    if not os.path.exists(shim_lib_path(64)):
+        return None
+    sk64 = Skred(64, device=device, max_frames=512)
+    W.install(sk64, W.config2(64, seconds=60.0, luts=load_luts()))
+    out = np.zeros((512, 2), dtype=np.float32)
+    for _ in range(50):
+        sk64.lib.synth(out.ctypes.data, None, 512, 2, None)
+    return block_latency(sk64, nblocks)
 
 
 def cpu_baseline(V):

@@ -266,6 +266,8 @@ typedef struct skb_stats {
   double   host_us[4];        /* diagnostics, host microseconds accumulated: [0] launching a batch (sorting its ops, staging,
                                  H2D, kernel launches), [1] queueing skb_finish (wait for staging, gain H2D, k_finish, D2H),
                                  [2] waiting for the stream in skb_finish, [3] unused */
+  uint64_t h2d_bytes, d2h_bytes; /* bytes the render path copied host -> device (parameter records, ops, per-launch staging
+                                    block, noise and gain traces) and device -> host (stereo block, counters, tap) */
 } skb_stats;
 int  skb_get_stats(skb_engine *e, skb_stats *out);
 

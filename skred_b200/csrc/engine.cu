@@ -788,6 +788,7 @@ static int sync_inputs(skb_engine *e, cudaStream_t st, bool defer_ops = false) {
     if (cnt) {
       CK(cudaMemcpyAsync(e->d_idx, e->h_idx, cnt * sizeof(int), cudaMemcpyHostToDevice, st));
       CK(cudaMemcpyAsync(e->d_recs, e->h_recs, cnt * SKB_NPQ * sizeof(float4), cudaMemcpyHostToDevice, st));
+      e->stats.h2d_bytes += (uint64_t)(cnt * (SKB_NPQ * sizeof(float4) + sizeof(int)));
       const int total = (int)cnt * SKB_NPQ;
       k_scatter_params<<<(total + 255) / 256, 256, 0, st>>>(e->d_pq, e->cap, e->d_idx, e->d_recs, (int)cnt);
       e->stats.kernel_launches++;
@@ -826,6 +827,7 @@ static int sync_inputs(skb_engine *e, cudaStream_t st, bool defer_ops = false) {
       }
       CK(cudaMemcpyAsync(e->d_ops, e->h_ops, cnt * sizeof(skb_op), cudaMemcpyHostToDevice, st));
       CK(cudaMemcpyAsync(e->d_runs, e->h_runs, (size_t)nruns * sizeof(int2), cudaMemcpyHostToDevice, st));
+      e->stats.h2d_bytes += (uint64_t)(cnt * sizeof(skb_op) + (size_t)nruns * sizeof(int2));
       k_apply_ops<<<(nruns + 127) / 128, 128, 0, st>>>(e->d_sq[e->cur], e->cap, e->d_ops, e->d_runs, nruns);
       e->stats.kernel_launches++;
       CK(cudaEventRecord(e->ev_h2d, st));
@@ -922,10 +924,13 @@ static int batch_launch(skb_engine *e) {
     e->batch.wake_words.clear();
   }
   CK(cudaMemcpyAsync(ds, hs, stage_bytes, cudaMemcpyHostToDevice, e->copy_stream));
+  e->stats.h2d_bytes += (uint64_t)(stage_bytes);
   CK(cudaEventRecord(e->ev_stage_copied[sb], e->copy_stream));
   CK(cudaStreamWaitEvent(st, e->ev_stage_copied[sb], 0));
-  if (e->any_noise)
+  if (e->any_noise) {
     CK(cudaMemcpyAsync(e->d_noise, e->h_noise, (size_t)nframes * sizeof(float), cudaMemcpyHostToDevice, st));
+    e->stats.h2d_bytes += (uint64_t)((size_t)nframes * sizeof(float));
+  }
   CK(cudaEventRecord(e->ev_h2d, st));
   const skb_engine::RowList lb = wide ? e->list_b[nwin] : skb_engine::RowList();
   const int groups_b = wide ? lb.ctas * (lb.rows_cap / SKB_CTA_WARPS) : 0;
@@ -1103,10 +1108,12 @@ int skb_finish(skb_engine *e, const float *d_mix, int nframes, const float *gain
   if (wait_staging(e)) return e->err;
   memcpy(e->h_gain, gain, (size_t)nframes * sizeof(float));
   CK(cudaMemcpyAsync(e->d_gain, e->h_gain, (size_t)nframes * sizeof(float), cudaMemcpyHostToDevice, st));
+  e->stats.h2d_bytes += (uint64_t)((size_t)nframes * sizeof(float));
   CK(cudaEventRecord(e->ev_h2d, st));
   k_finish<<<(nframes + 255) / 256, 256, 0, st>>>((const float2 *)d_mix, e->d_gain, e->d_out, nframes);
   e->stats.kernel_launches++;
   CK(cudaMemcpyAsync(e->h_out, e->d_out, (size_t)nframes * sizeof(float2), cudaMemcpyDeviceToHost, st));
+  e->stats.d2h_bytes += (uint64_t)nframes * sizeof(float2) + SKB_N_COUNTERS * sizeof(unsigned long long);
   CK(cudaMemcpyAsync(e->h_counters, e->d_counters, SKB_N_COUNTERS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   const double t_f1 = host_now_us();
   CK(cudaStreamSynchronize(st));
@@ -1186,6 +1193,7 @@ int skb_read_tap(skb_engine *e, int frame0, int nframes, float *out) {
   cudaStream_t st = e->last_stream ? e->last_stream : e->stream;
   /* straight into the caller's (pageable) buffer: the copy is as large as the tap itself */
   CK(cudaMemcpyAsync(out, e->d_tap + (size_t)frame0 * e->n, (size_t)nframes * e->n * sizeof(float2), cudaMemcpyDeviceToHost, st));
+  e->stats.d2h_bytes += (uint64_t)nframes * e->n * sizeof(float2);
   CK(cudaStreamSynchronize(st));
   return e->err;
 }
