@@ -30,7 +30,8 @@ REF = os.environ.get("SKRED_REF", "/root/reference")
 GOLD_FRAMES = 8 * 512
 PATCHES = [0, 1, 3, 5, 7, 8, 15, 16, 17, 21, 23, 26, 29, 30, 31, 41, 42, 64, 71, 73]
 # patches that load user samples with `:wN,slot` (wire.c:406-441): the wav files they name travel as fixtures
-WAV_PATCHES = {13: [13, 16], 36: [3], 38: [17, 9], 44: [19]}
+WAV_PATCHES = {13: [13, 16], 36: [3], 38: [17, 9], 44: [19], 10: [24, 23, 22, 21], 20: [24, 23], 43: [32, 33, 3],
+               47: [24, 30, 31, 32], 69: [17, 9]}
 
 
 def parse_tables(path, ctype):

@@ -377,3 +377,25 @@ def test_wav_patch_vs_golden(n, golden_wav_patches, tmp_path):
     assert maxdiff(out, gold) <= FULL_SCALE_TOL
     assert np.array_equal(ph.view(np.uint32), golden_wav_patches["p%d_phase" % n].view(np.uint32)), "phase trace"
     assert np.array_equal(fin, golden_wav_patches["p%d_finished" % n]), "finished trace"
+
+
+def test_voice_tap_1024_voices_batched_vs_port(luts):
+    """The tap at 1,024 voices with 4,096-frame calls (8 windows per launch, events applied in-kernel at the
+    boundaries, voices skipped / woken inside the launch): bit for bit against the CPU restatement fed the
+    same timestamped queue one callback at a time."""
+    from skred_b200 import workloads as W
+    V, frames = 1024, 3 * 4096
+    wl = W.config5(V, seconds=600.0, luts=luts, event_seconds=frames / 44100.0 + 1.0, stationary=True)
+    wl["timed"] = sorted(wl["timed"] + [(int((0.04 + 0.33 * (v % 7) / 7.0) * 44100), ("voice_trigger", v) if v % 3 == 2
+                                         else ("envelope_velocity", v, float(v % 2))) for v in range(V)], key=lambda x: x[0])
+    a, b = O.PortSkred(V, run_seq=False), O.DropinCuda(V, run_seq=False)
+    a.enable_tap(512)
+    b.enable_tap(4096)
+    for s in (a, b):
+        W.install(s, wl)
+        _queue(s, wl["timed"])
+    oa, ta = a.render_with_tap(frames, block=512)
+    ob, tb = b.render_with_tap(frames, block=4096)
+    assert maxdiff(oa, ob) <= FULL_SCALE_TOL
+    assert np.array_equal(ta.view(np.uint32), tb.view(np.uint32))
+    assert float(np.abs(ta).max()) > 0.0 and int(np.count_nonzero(np.abs(ta).sum(axis=(0, 2)) == 0.0)) > 0   # some voices silent

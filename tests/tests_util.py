@@ -4,7 +4,7 @@ PATCH_IDS = [0, 1, 3, 5, 7, 8, 15, 16, 17, 21, 23, 26, 29, 30, 31, 41, 42, 64, 7
 FULL_SCALE_TOL = 1e-5      # north_star: within 1e-5 of full scale (1.0) per sample on float paths
 
 
-WAV_PATCH_IDS = [13, 36, 38, 44]     # shipped patches that load user samples with `:wN,slot` (wire.c:406-441)
+WAV_PATCH_IDS = [10, 13, 20, 36, 38, 43, 44, 47, 69]     # shipped patches that load user samples with `:wN,slot` (wire.c:406-441)
 
 
 def load_wav_patch(s, golden_wav, n, tmpdir):
