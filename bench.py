@@ -430,6 +430,15 @@ def own_arm(a):
     traffic = float(ncu["dram_bytes_read"] + ncu["dram_bytes_write"]) if ncu else None
     issue_peak = N_SM * 4 * sm_mhz * 1e6                     # warp instructions per second: 4 schedulers per SM
 
+    weak = None
+    if world > 1 and not a.no_weak:
+        w_act, w_ms = weak_scaling_leg(a, local, world, stream, sp)
+        weak = {"value": w_act / (w_ms * 1e-3), "unit": UNIT, "voices_per_gpu": V, "voices_total": V * world,
+                "ms_per_step": w_ms / a.steps, "steps": a.steps,
+                "note": "same loop as `value` with every GPU rendering a full %d-voice job (an N x %d-voice render, per-GPU work "
+                        "fixed): the strong-scaling headline divides ONE %d-voice job, whose launch cannot be shorter than its "
+                        "slowest voice's sequential frames" % (V, V, V)}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -466,6 +475,7 @@ def own_arm(a):
                                                                 "fire_events": host_ms[2], "finish_launch_kernels_d2h_sync": host_ms[3],
                                                                 "of_which_launch_host": eng_us[0] * 1e-3, "finish_enqueue": eng_us[1] * 1e-3,
                                                                 "stream_wait": eng_us[2] * 1e-3}},
+            "weak_scaling": weak,
             "gpu_launches": launches,
             "clocks": clk,
             "block_latency_ms_p50": None,
@@ -480,6 +490,66 @@ def own_arm(a):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def weak_scaling_leg(a, local, world, stream, sp):
+    """N > 1 only, reported beside the strong-scaling headline: every GPU renders a full V-voice job (rank r holds voices
+    r*V ... (r+1)*V - 1 of an N*V-voice render; the V-voice load is periodic in v by construction, so every rank installs
+    the same recipe on its own engine), partial mixes summed with the NCCL reduce overlapping the next render like the
+    headline loop.  Returns (rendered voice-frames over all ranks, device ms (max over ranks), steps)."""
+    import torch
+    import torch.distributed as dist
+    from skred_b200 import Skred
+    from skred_b200.host import load_engine_lib
+    V, F, LF = a.voices, a.frames, a.launch_frames
+    eng = load_engine_lib()
+    sk = Skred(V, device=local, rank=0, world=1, max_frames=max(F, 512), private=True)
+    total_frames = (a.warmup + a.steps) * F + 4 * F
+    wl = W.config5(V, seconds=600.0, luts=load_luts(), event_seconds=total_frames / SR + 1.0, stationary=True)
+    W.install(sk, wl)
+    ev = W.to_skb_events(wl["timed"])
+    sk.lib.skb_shim_queue_events.argtypes = [C.c_void_p, C.c_int]
+    sk.lib.skb_shim_queue_events(ev.ctypes.data, len(ev))
+    sk.flush()
+    sk.lib.skb_shim_render_calls.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    comm = torch.cuda.Stream()
+    mix = [torch.zeros((F, 2), dtype=torch.float32, device="cuda") for _ in range(2)]
+    rendered = [torch.cuda.Event() for _ in mix]
+    reduced = [torch.cuda.Event() for _ in mix]
+
+    def step(i):
+        k = i % 2
+        stream.wait_event(reduced[k])
+        if sk.lib.skb_shim_render_calls(LF, F // LF, mix[k].data_ptr(), sp) != 0:
+            raise RuntimeError("render failed")
+        rendered[k].record(stream)
+        with torch.cuda.stream(comm):
+            comm.wait_event(rendered[k])
+            dist.reduce(mix[k], dst=0, op=dist.ReduceOp.SUM)
+            reduced[k].record(comm)
+        sk.lib.skb_shim_discard_gain()
+
+    for i in range(a.warmup):
+        step(i)
+    stream.wait_stream(comm)
+    dist.barrier()
+    torch.cuda.synchronize()
+    eng.skb_sync(sk.engine, sp)
+    before = sk.stats().active_voice_frames
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(a.steps):
+        step(a.warmup + i)
+    stream.wait_stream(comm)
+    e1.record(stream)
+    dist.barrier()
+    torch.cuda.synchronize()
+    eng.skb_sync(sk.engine, sp)
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    n = torch.tensor([float(sk.stats().active_voice_frames - before)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    return float(n.item()), float(t.item())
 
 
 def block_latency(sk, nblocks):
@@ -532,6 +602,7 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling companion measurement")
     ap.add_argument("--latency-blocks", type=int, default=1000)
     a = ap.parse_args()
     if a.warmup < 3:
