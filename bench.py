@@ -62,6 +62,26 @@ def load_peaks():
     return 6650.0, 1965.0, "fallback"
 
 
+_JSON_FD = None
+
+
+def quiet_stdout():
+    """bench.py's stdout carries ONE JSON line: everything else that writes to fd 1 while it runs — the reference's
+    and the shim's `# make w0 sine ...` start-up lines (synth.c:1203-1290 prints them), NCCL's version banner when
+    NCCL_DEBUG is set on the box — goes to stderr instead.  Spawned worker processes inherit the redirected fd."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
+
 def load_ncu_counters():
     """Per-launch counters of the dominant kernel from the committed ncu capture of this same command
     (profiles/): DRAM bytes for roofline.traffic, warp instructions for the issue-slot roofline."""
@@ -182,7 +202,7 @@ def reference_arm(a):
     shard = 4096 if V >= 4096 else V
     from oracle import oracle as O
     if not O.have_ref(shard):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libskred_ref_v%d.so not built" % shard}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libskred_ref_v%d.so not built" % shard})
         return 0
     cores = os.cpu_count() or 1
     # bounded sample: 4 callbacks per step; with W >= 3 the warm-up (>= 6,144 frames) gets past the attack + decay
@@ -202,7 +222,7 @@ def reference_arm(a):
         "e2e": {"value": vps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -485,7 +505,7 @@ def own_arm(a):
             line["block_latency_ms_p50_64_voices"] = block_latency_small(local, a.latency_blocks)
         if world == 1 and not a.no_cpu:
             line["cpu_baseline"] = cpu_baseline(V)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -607,6 +627,8 @@ def main():
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3
+    if not (a.impl == "own" and a.gpus > 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1):
+        quiet_stdout()                       # (the torchrun re-launch convenience leaves it to its children)
     if a.impl == "reference":
         return reference_arm(a)
     world = int(os.environ.get("WORLD_SIZE", "1"))
