@@ -1,0 +1,93 @@
+"""Random TIMESTAMPED event streams of every device event code (include/skred_b200_shim.h skb_event: trigger,
+velocity, freq, midi note, amp, pan, wave, CZ, filter freq / res, mute) over a mixed 1,024-voice load.
+
+The product takes the whole stream through skb_shim_queue_events and renders 4,096-frame calls: the engine decides
+per boundary whether the events can be applied inside the running launch (state edits) or end the batch
+(parameter records, re-plans), and must land every one of them on its 512-frame boundary.
+CPU: the shim over the CPU restatement against the compiled reference fed the same events callback by callback
+through its setters.  GPU: the CUDA drop-in against the same reference."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from skred_b200 import workloads as W
+from tests_util import assert_state_equal, FULL_SCALE_TOL
+import full_size as FS
+
+V = 1024
+EXACT = ("phase", "finished", "sh_hold", "sh_count", "env_active", "env_start", "env_release",
+         "sample", "filter_xy", "smoother_gain", "pan_left", "pan_right")
+
+
+def random_events(rng, frames, n):
+    waves = [0, 1, 2, 3, 4, 5, 33, 40, 47, 62, 100, 111, 140, 166, 200, 201, 202]
+    out = []
+    for _ in range(n):
+        when = int(rng.randint(0, frames))
+        v = int(rng.randint(0, V))
+        k = rng.randint(0, 14)
+        if k <= 2:
+            c = ("voice_trigger", v)
+        elif k <= 5:
+            c = ("envelope_velocity", v, float(rng.choice([0.0, 1.0, 0.5])))
+        elif k == 6:
+            c = ("freq_set", v, float(np.float32(rng.uniform(30.0, 3000.0))))
+        elif k == 7:
+            c = ("freq_midi", v, float(rng.randint(30, 90)))
+        elif k == 8:
+            c = ("amp_set", v, float(np.float32(rng.choice([0.0, 0.02, 0.04]))))
+        elif k == 9:
+            c = ("pan_set", v, float(np.float32(rng.uniform(-1.0, 1.0))))
+        elif k == 10:
+            c = ("wave_set", v, int(waves[rng.randint(len(waves))]))
+        elif k == 11:
+            c = ("cz_set", v, int(rng.randint(0, 8)), float(np.float32(rng.uniform(0.0, 1.0))))
+        elif k == 12:
+            c = ("mmf_set_freq", v, float(np.float32(rng.uniform(100.0, 8000.0)))) if rng.rand() < 0.6 else \
+                ("mmf_set_res", v, float(np.float32(rng.uniform(0.3, 8.0))))
+        else:
+            c = ("wave_mute", v, int(rng.randint(0, 2)))
+        out.append((when, c))
+    out.sort(key=lambda x: x[0])
+    return out
+
+
+def _calls_for_reference(timed):
+    # skb_event carries wave / cz mode / mute as floats (a0); the setters take ints
+    ev = W.bucket(timed)
+    return ev
+
+
+def run(seed, make_dut, luts, frames=5 * 4096 + 700, n_events=2500, call=4096):
+    rng = np.random.RandomState(seed)
+    wl = W.config5(V, seconds=600.0, luts=luts, event_seconds=frames / 44100.0 + 1.0, stationary=True)
+    timed = sorted(wl["timed"] + random_events(rng, frames, n_events), key=lambda x: x[0])
+    ref, dut = O.RefSkred(V, run_seq=False), make_dut(V, run_seq=False)
+    W.install(ref, wl)
+    W.install(dut, wl)
+    FS.queue_events(dut, timed)
+    want = ref.render(frames, block=512, events=W.bucket(timed))
+    got = dut.render(frames, block=call)
+    err = float(np.max(np.abs(want.astype(np.float64) - got)))
+    assert err <= FULL_SCALE_TOL, err
+    assert float(np.abs(want).max()) > 1e-3
+    assert_state_equal(ref.state(), dut.state(), exact_keys=EXACT)
+    return dut
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_random_event_stream_shim_queue_vs_reference_callbacks(seed, luts):
+    import os
+    if not (O.have_ref(V) and os.path.exists(O.port_lib_path(V))):
+        pytest.skip("oracle libraries for 1,024 voices not built")
+    run(seed, O.PortSkred, luts)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,call", [(11, 4096), (12, 4096), (13, 8192), (14, 512), (15, 1536), (16, 4096)])
+def test_random_event_stream_cuda_vs_reference(seed, call, luts):
+    if not O.have_ref(V):
+        pytest.skip("compiled reference for 1,024 voices not present")
+    dut = run(seed, O.DropinCuda, luts, call=call)
+    st = dut.engine_stats()
+    assert st.ops_applied > 0
