@@ -14,7 +14,7 @@
         force-include it (`gcc -include`): its include guard then masks the
         original when synth.c does `#include "skred.h"`;
       * notamy/pcm_samples_large.h is missing from the checkout:
-        oracle/gen_pcm_stub.py writes a seeded synthetic stand-in into
+        tools/gen_pcm_stub.py writes a seeded synthetic stand-in into
         build/gen/.
     Skipped (with a message) when /root/reference is absent — the GPU box
     uses the prebuilt files.
@@ -67,7 +67,7 @@ def gen_common():
     """pcm stub + nothing else; idempotent."""
     hdr = os.path.join(GEN, "pcm_samples_large.h")
     if not os.path.exists(hdr):
-        sys.path.insert(0, HERE)
+        sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tools"))
         import gen_pcm_stub
         gen_pcm_stub.main(REF, GEN)
     return hdr

@@ -104,11 +104,11 @@ def _gen_skred_h(v):
 
 def _amysamples_o(v):
     """The AMY PCM map + blob of the skred tree (amysamples.c).  The 1.17 M-sample
-    pcm[] header is missing from this checkout; oracle/gen_pcm_stub.py
+    pcm[] header is missing from this checkout; tools/gen_pcm_stub.py
     writes the seeded synthetic stand-in both sides of every parity test share."""
     hdr = os.path.join(GEN, "pcm_samples_large.h")
     if not os.path.exists(hdr):
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
         import gen_pcm_stub
         gen_pcm_stub.main(SKRED_SRC, GEN)
     amy_o = os.path.join(GEN, "amysamples.o")

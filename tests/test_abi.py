@@ -79,6 +79,6 @@ def test_no_cpu_fallback():
 def test_product_never_references_the_oracle():
     for d, _, files in os.walk(os.path.join(ROOT, "skred_b200")):
         for f in files:
-            if f.endswith((".py", ".c", ".cu", ".cuh", ".h")) and f != "build.py":
+            if f.endswith((".py", ".c", ".cu", ".cuh", ".h")) :
                 txt = open(os.path.join(d, f)).read()
-                assert "oracle" not in txt.replace("oracle/gen_pcm_stub", ""), os.path.join(d, f)
+                assert "oracle" not in txt, os.path.join(d, f)
