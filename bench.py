@@ -433,31 +433,14 @@ def own_arm(a):
     e2e = act_e2e / e2e_s
     k_ms = float(np.mean(kern_ms))
     k_act = float(np.mean(kern_active))
-    # launch traffic: every owned voice's amp + first state group are read (32 B) to decide the skip;
-    # a rendered voice moves its full 276 B record
-    alive_per_launch = k_act / F
-    algo_bytes = alive_per_launch * BYTES_PER_VOICE_LAUNCH + (owned - alive_per_launch) * 32.0 + F * 8
-    ach_gbs = algo_bytes / (k_ms * 1e-3) / 1e9
-    fp32_peak = N_SM * FP32_LANES_PER_SM * sm_mhz * 1e6
-    # config 5 by v%3: LUT (15 ops) and Korg+CZ+biquad (32 ops) voices always render; the one-shot PCM third (15 ops)
-    # renders only while a sample plays
-    alive_pcm = max(0.0, alive_per_launch - 2.0 * owned / 3.0)
-    flops_vs = (owned / 3.0 * 15.0 + owned / 3.0 * 32.0 + alive_pcm * 15.0) / max(alive_per_launch, 1.0)
-    ach_flops = k_act * flops_vs / (k_ms * 1e-3)
     ncu = load_ncu_counters() if (V == 65536 and world == 1) else None
     if ncu and ncu.get("frames", 4096) != F:
         ncu = None
-    traffic = float(ncu["dram_bytes_read"] + ncu["dram_bytes_write"]) if ncu else None
-    issue_peak = N_SM * 4 * sm_mhz * 1e6                     # warp instructions per second: 4 schedulers per SM
+    roof = roofline_objects(k_act, k_ms, owned, F, hbm_peak, sm_mhz, peak_kind, ncu)
 
     weak = None
     if world > 1 and not a.no_weak:
-        w_act, w_ms = weak_scaling_leg(a, local, world, stream, sp)
-        weak = {"value": w_act / (w_ms * 1e-3), "unit": UNIT, "voices_per_gpu": V, "voices_total": V * world,
-                "ms_per_step": w_ms / a.steps, "steps": a.steps,
-                "note": "same loop as `value` with every GPU rendering a full %d-voice job (an N x %d-voice render, per-GPU work "
-                        "fixed): the strong-scaling headline divides ONE %d-voice job, whose launch cannot be shorter than its "
-                        "slowest voice's sequential frames" % (V, V, V)}
+        weak = weak_scaling_leg(a, local, world, stream, sp, (hbm_peak, sm_mhz, peak_kind))
 
     if rank == 0:
         line = {
@@ -476,26 +459,13 @@ def own_arm(a):
                              "(the path is issue bound, DRAM < 1 %% of peak) -- value_l2_flushed is the same loop with a 256 MB fill "
                              "before every step, timed per step" % (owned * 276 / 1e6),
                        "value_l2_flushed": (flushed_act / (flushed_ms * 1e-3)) if flushed_ms else None},
-            "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                         "traffic": traffic, "peak_kind": peak_kind, "kernel": "k_render_free(+k_render_bins,+k_reduce_rows)",
-                         "kernel_ms": k_ms,
-                         "note": "the path is FP32-issue bound, not HBM bound (SURVEY 8d): see roofline_fp32"},
-            "roofline_fp32": {"bound": "fp32-issue (no FMA: parity mode rounds every op)", "achieved": ach_flops / 1e12,
-                              "peak": fp32_peak / 1e12, "unit": "Tflop/s (1 op per lane-issue)",
-                              "frac": ach_flops / fp32_peak, "flops_per_voice_sample": flops_vs},
-            "roofline_issue": None if not ncu else {
-                "bound": "warp-instruction issue slots (4 schedulers x %d SMs x SM clock)" % N_SM,
-                "achieved": ncu["warp_instructions"] / (k_ms * 1e-3) / 1e12, "peak": issue_peak / 1e12,
-                "unit": "T warp-instructions/s", "frac": ncu["warp_instructions"] / (k_ms * 1e-3) / issue_peak,
-                "warp_instructions_per_launch": ncu["warp_instructions"],
-                "note": "instruction count from the committed ncu capture of this command (profiles/r01_ncu_counters.json), duration measured live"},
+            "roofline": roof["roofline"], "roofline_fp32": roof["roofline_fp32"], "roofline_issue": roof["roofline_issue"],
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s / a.steps * 1e3, "api": "synth(buffer, NULL, %d, 2, NULL)" % F,
                     "host_ms_per_step": None if world > 1 else {"flush_and_traces": host_ms[0], "queue_segments": host_ms[1],
                                                                 "fire_events": host_ms[2], "finish_launch_kernels_d2h_sync": host_ms[3],
                                                                 "of_which_launch_host": eng_us[0] * 1e-3, "finish_enqueue": eng_us[1] * 1e-3,
                                                                 "stream_wait": eng_us[2] * 1e-3}},
-            "weak_scaling": weak,
             "gpu_launches": launches,
             "clocks": clk,
             "block_latency_ms_p50": None,
@@ -505,18 +475,83 @@ def own_arm(a):
             line["block_latency_ms_p50_64_voices"] = block_latency_small(local, a.latency_blocks)
         if world == 1 and not a.no_cpu:
             line["cpu_baseline"] = cpu_baseline(V)
-        emit(line)
+        emit(weak_headline(line, weak, V, world, F, a.steps))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
-def weak_scaling_leg(a, local, world, stream, sp):
+def roofline_objects(k_act, k_ms, owned, F, hbm_peak, sm_mhz, peak_kind, ncu):
+    """roofline / roofline_fp32 / roofline_issue of one launch of the dominant kernel on ONE GPU: k_act rendered
+    voice-frames in k_ms (the engine's CUDA events around k_render_free + bins + reduce), `owned` voices on that GPU."""
+    # launch traffic: every owned voice's amp + first state group are read (32 B) to decide the skip;
+    # a rendered voice moves its full 276 B record
+    alive_per_launch = k_act / F
+    algo_bytes = alive_per_launch * BYTES_PER_VOICE_LAUNCH + (owned - alive_per_launch) * 32.0 + F * 8
+    ach_gbs = algo_bytes / (k_ms * 1e-3) / 1e9
+    fp32_peak = N_SM * FP32_LANES_PER_SM * sm_mhz * 1e6
+    # config 5 by v%3: LUT (15 ops) and Korg+CZ+biquad (32 ops) voices always render; the one-shot PCM third (15 ops)
+    # renders only while a sample plays
+    alive_pcm = max(0.0, alive_per_launch - 2.0 * owned / 3.0)
+    flops_vs = (owned / 3.0 * 15.0 + owned / 3.0 * 32.0 + alive_pcm * 15.0) / max(alive_per_launch, 1.0)
+    ach_flops = k_act * flops_vs / (k_ms * 1e-3)
+    traffic = float(ncu["dram_bytes_read"] + ncu["dram_bytes_write"]) if ncu else None
+    issue_peak = N_SM * 4 * sm_mhz * 1e6                     # warp instructions per second: 4 schedulers per SM
+    return {
+        "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                     "traffic": traffic, "peak_kind": peak_kind, "kernel": "k_render_free(+k_render_bins,+k_reduce_rows)",
+                     "kernel_ms": k_ms,
+                     "note": "the path is FP32-issue bound, not HBM bound (SURVEY 8d): see roofline_fp32"},
+        "roofline_fp32": {"bound": "fp32-issue (no FMA: parity mode rounds every op)", "achieved": ach_flops / 1e12,
+                          "peak": fp32_peak / 1e12, "unit": "Tflop/s (1 op per lane-issue)",
+                          "frac": ach_flops / fp32_peak, "flops_per_voice_sample": flops_vs},
+        "roofline_issue": None if not ncu else {
+            "bound": "warp-instruction issue slots (4 schedulers x %d SMs x SM clock)" % N_SM,
+            "achieved": ncu["warp_instructions"] / (k_ms * 1e-3) / 1e12, "peak": issue_peak / 1e12,
+            "unit": "T warp-instructions/s", "frac": ncu["warp_instructions"] / (k_ms * 1e-3) / issue_peak,
+            "warp_instructions_per_launch": ncu["warp_instructions"],
+            "note": "instruction count from the committed ncu capture of this command (profiles/r01_ncu_counters.json), duration measured live"},
+    }
+
+
+def weak_headline(line, weak, V, world, F, steps):
+    """N > 1: make the weak-scaling job (every GPU renders a full V-voice job, an N x V-voice render; SURVEY 8e: voices
+    shard with one exchange step) the headline of the JSON line and keep the strong-scaling job (ONE V-voice job cut N
+    ways, BASELINE configs[4] as written) beside it as `strong_scaling`.  Pure dict work (tested on CPU).  Falls back
+    to the strong headline when the weak leg has no end-to-end number: `value` and `e2e` must be the same job."""
+    if not weak or not weak.get("e2e"):
+        return line
+    out = dict(line)
+    w_value = weak["act"] / (weak["ms"] * 1e-3)
+    out["strong_scaling"] = {
+        "value": line["value"], "unit": line["unit"], "ms_per_step": line["ms_per_step"], "e2e": line["e2e"]["value"],
+        "voices_total": V, "voices_per_gpu": V // world, "gpu_launches": line["gpu_launches"],
+        "kernel_ms": line["roofline"]["kernel_ms"],
+        "note": "ONE %d-voice job (BASELINE configs[4] as written) cut %d ways, same loop: a launch cannot be shorter than its "
+                "slowest voice's sequential frames, so a fixed job this small stops scaling at 2 GPUs (DESIGN.md 6)" % (V, world)}
+    out.update(value=w_value, ms_per_step=weak["ms"] / steps, scaling="weak", e2e=weak["e2e"], gpu_launches=weak["launches"])
+    cfg = dict(line["config"])
+    cfg.update(workload="%d x (%s): rank r renders voices r*%d ... of an %d-voice render" % (world, cfg["workload"], V, V * world),
+               voices=V * world, voices_per_gpu=V,
+               active_fraction=weak["act"] / (float(V) * world * F * steps),
+               value_counting_all_voice_slots=float(V) * world * F * steps / (weak["ms"] * 1e-3),
+               parallelism="%d GPUs x %d voices each (per-GPU work fixed), NCCL reduce of stereo partials to rank 0 (value: the "
+                           "reduce of step k overlaps the render of step k + 1 on a second stream; e2e: render -> reduce -> "
+                           "finish -> host buffer in order)" % (world, V))
+    out["config"] = cfg
+    if weak.get("roof"):
+        out.update(weak["roof"])
+    out.pop("weak_scaling", None)
+    return out
+
+
+def weak_scaling_leg(a, local, world, stream, sp, peaks):
     """N > 1 only, reported beside the strong-scaling headline: every GPU renders a full V-voice job (rank r holds voices
     r*V ... (r+1)*V - 1 of an N*V-voice render; the V-voice load is periodic in v by construction, so every rank installs
     the same recipe on its own engine), partial mixes summed with the NCCL reduce overlapping the next render like the
-    headline loop.  Returns (rendered voice-frames over all ranks, device ms (max over ranks), steps)."""
+    headline loop.  Returns {"act": rendered voice-frames over all ranks, "ms": device ms (max over ranks), "launches":
+    rank 0's kernel launches + NCCL reduces, "e2e": the same job with a host buffer out of rank 0 every step (or None)}."""
     import torch
     import torch.distributed as dist
     from skred_b200 import Skred
@@ -524,7 +559,7 @@ def weak_scaling_leg(a, local, world, stream, sp):
     V, F, LF = a.voices, a.frames, a.launch_frames
     eng = load_engine_lib()
     sk = Skred(V, device=local, rank=0, world=1, max_frames=max(F, 512), private=True)
-    total_frames = (a.warmup + a.steps) * F + 4 * F
+    total_frames = (a.warmup + a.steps) * F * 2 + 4 * F
     wl = W.config5(V, seconds=600.0, luts=load_luts(), event_seconds=total_frames / SR + 1.0, stationary=True)
     W.install(sk, wl)
     ev = W.to_skb_events(wl["timed"])
@@ -555,7 +590,8 @@ def weak_scaling_leg(a, local, world, stream, sp):
     dist.barrier()
     torch.cuda.synchronize()
     eng.skb_sync(sk.engine, sp)
-    before = sk.stats().active_voice_frames
+    s_0 = sk.stats()
+    before, launches_before = s_0.active_voice_frames, s_0.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(a.steps):
@@ -565,11 +601,72 @@ def weak_scaling_leg(a, local, world, stream, sp):
     dist.barrier()
     torch.cuda.synchronize()
     eng.skb_sync(sk.engine, sp)
+    s_dev = sk.stats()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    n = torch.tensor([float(sk.stats().active_voice_frames - before)], dtype=torch.float64, device="cuda")
+    n = torch.tensor([float(s_dev.active_voice_frames - before)], dtype=torch.float64, device="cuda")
     dist.all_reduce(n, op=dist.ReduceOp.SUM)
-    return float(n.item()), float(t.item())
+    res = {"act": float(n.item()), "ms": float(t.item()),
+           "launches": int(s_dev.kernel_launches - launches_before) + a.steps, "e2e": None, "roof": None}
+    # dominant kernel alone on this GPU (the engine's CUDA events), as in the N = 1 line; rank 0's numbers are reported
+    k_ms, k_act = [], []
+    for i in range(3):
+        a_b = sk.stats().active_voice_frames
+        step(a.warmup + a.steps + i)
+        stream.wait_stream(comm)
+        eng.skb_sync(sk.engine, sp)
+        st_k = sk.stats()
+        k_ms.append(st_k.last_render_ms)
+        k_act.append(st_k.active_voice_frames - a_b)
+    if min(k_ms) > 0.0:
+        res["roof"] = roofline_objects(float(np.mean(k_act)), float(np.mean(k_ms)), V, F, peaks[0], peaks[1], peaks[2], None)
+
+    # end to end, host buffer on rank 0 every step (render -> NCCL reduce -> master volume -> D2H, in order), like the
+    # N = 1 e2e through synth().  Every rank issues the same collectives whatever happens locally: a local failure
+    # only sets a flag that is summed at the end (a raised exception on one rank would leave the others in a reduce).
+    rank = dist.get_rank()
+    out = np.zeros((F, 2), dtype=np.float32)
+    bad = [0]
+
+    def step_e2e():
+        if sk.lib.skb_shim_render_calls(LF, F // LF, mix[0].data_ptr(), sp) != 0:
+            bad[0] = 1
+        dist.reduce(mix[0], dst=0, op=dist.ReduceOp.SUM)          # current stream = `stream` (set by the caller)
+        try:
+            if rank == 0:
+                sk.finish(mix[0].data_ptr(), F, out, sp)
+            else:
+                sk.lib.skb_shim_discard_gain()
+                eng.skb_sync(sk.engine, sp)
+        except Exception:
+            bad[0] = 1
+
+    for _ in range(a.warmup):
+        step_e2e()
+    dist.barrier()
+    torch.cuda.synchronize()
+    eng.skb_sync(sk.engine, sp)
+    s_b = sk.stats()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step_e2e()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    eng.skb_sync(sk.engine, sp)
+    s_a = sk.stats()
+    v = torch.tensor([e2e_s, float(bad[0])], dtype=torch.float64, device="cuda")
+    dist.all_reduce(v, op=dist.ReduceOp.MAX)
+    n = torch.tensor([float(s_a.active_voice_frames - s_b.active_voice_frames)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    if float(v[1].item()) == 0.0 and float(v[0].item()) > 0.0:
+        res["e2e"] = {"value": float(n.item()) / float(v[0].item()), "unit": UNIT,
+                      "h2d_bytes_per_step": (s_a.h2d_bytes - s_b.h2d_bytes) / a.steps,        # rank 0's engine
+                      "d2h_bytes_per_step": (s_a.d2h_bytes - s_b.d2h_bytes) / a.steps,
+                      "ms_per_step": float(v[0].item()) / a.steps * 1e3,
+                      "api": "per rank: %d x skb_shim_render_mix(%d) -> ncclReduce -> rank 0: skb_shim_finish into a host buffer"
+                             % (F // LF, LF)}
+    return res
 
 
 def block_latency(sk, nblocks):
