@@ -20,6 +20,12 @@ block boundaries.  One STEP = one batch of `--frames` frames
   cpu_baseline  the compiled reference (oracle/_ref) on ONE host core over a bounded
           sample (first 4096 voices of the same load).
 
+N > 1 (`scaling`: "weak", SURVEY §8e — voices shard with one exchange step): every GPU
+renders a full V-voice job, rank r holding voices r*V ... of an N*V-voice render, partial
+mixes summed to rank 0 by an NCCL reduce (value: overlapped with the next render; e2e: in
+order, host buffer out of rank 0 every step).  The ONE V-voice job cut N ways (BASELINE
+configs[4] as written) is measured in the same run and reported as `strong_scaling`.
+
 `--impl reference` times the reference's own synth.c (oracle/_ref, pinned flags)
 voice-sharded over ALL host cores (independent processes — the reference is
 single-threaded) on a bounded sample of the same workload.
@@ -211,9 +217,12 @@ def reference_arm(a):
     vps, sec, voices, procs, wall, frac = run_reference_cpu(V, frames, a.steps, a.warmup, cores, shard)
     line = {
         "impl": "reference", "metric": METRIC, "value": vps, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+        "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD % V,
+        "config": {"workload": (WORKLOAD % V) if a.gpus <= 1 else
+                   "%d x (%s), bounded sample: one %d-voice period of it (the own arm's N-GPU job repeats this load on every "
+                   "GPU; the reference's cost is linear in voices, its voice-samples/s does not depend on how many periods run)"
+                   % (a.gpus, WORKLOAD % V, V),
                    "voices": voices, "frames_per_step": frames, "active_fraction": frac,
                    "counting": "rendered voice-frames only: voices skipped by synth.c:531-542 (finished one-shots) do not count",
                    "parallelism": "%d independent reference processes x %d voices (reference is single-threaded)" % (procs, shard)},
@@ -411,7 +420,6 @@ def own_arm(a):
     eng_us = [(x - y) / a.steps for x, y in zip(sk.stats().host_us, s_b.host_us)]
     eng.skb_sync(sk.engine, sp)
     s_a = sk.stats()
-    clk = clocks.stop() if rank == 0 else None
     ops = int(s_a.ops_applied - s_b.ops_applied)
     par = int(s_a.params_uploaded - s_b.params_uploaded)
     # counted by the engine from the copies it issues (skb_stats.h2d_bytes / d2h_bytes): parameter records, the
@@ -441,11 +449,15 @@ def own_arm(a):
     weak = None
     if world > 1 and not a.no_weak:
         weak = weak_scaling_leg(a, local, world, stream, sp, (hbm_peak, sm_mhz, peak_kind))
+    clk = clocks.stop() if rank == 0 else None           # sampled over every timed region above, the weak leg included
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": dev_ms / a.steps, "higher_is_better": True,
+            # N = 1 is the first point of the weak-scaling series (V voices per GPU); at N > 1 this line is the ONE-job
+            # (strong) leg and weak_headline() below swaps the N x V-voice job in
+            "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD % V,
                        "voices": V, "frames_per_step": F, "frames_per_call": LF, "frames_per_launch": F, "block_frames": 512,
@@ -536,6 +548,8 @@ def weak_headline(line, weak, V, world, F, steps):
                voices=V * world, voices_per_gpu=V,
                active_fraction=weak["act"] / (float(V) * world * F * steps),
                value_counting_all_voice_slots=float(V) * world * F * steps / (weak["ms"] * 1e-3),
+               l2="state+params %.1f MB per launch and GPU, each word touched once per launch; not flushed between the timed "
+                  "steps (the path is issue bound, DRAM < 1 %% of peak; N = 1 reports value_l2_flushed)" % (V * 276 / 1e6),
                parallelism="%d GPUs x %d voices each (per-GPU work fixed), NCCL reduce of stereo partials to rank 0 (value: the "
                            "reduce of step k overlaps the render of step k + 1 on a second stream; e2e: render -> reduce -> "
                            "finish -> host buffer in order)" % (world, V))
@@ -619,7 +633,11 @@ def weak_scaling_leg(a, local, world, stream, sp, peaks):
         k_ms.append(st_k.last_render_ms)
         k_act.append(st_k.active_voice_frames - a_b)
     if min(k_ms) > 0.0:
-        res["roof"] = roofline_objects(float(np.mean(k_act)), float(np.mean(k_ms)), V, F, peaks[0], peaks[1], peaks[2], None)
+        # every GPU runs the N = 1 launch (V voices, F frames), so the committed ncu counters of that launch apply
+        ncu = load_ncu_counters() if V == 65536 else None
+        if ncu and ncu.get("frames", 4096) != F:
+            ncu = None
+        res["roof"] = roofline_objects(float(np.mean(k_act)), float(np.mean(k_ms)), V, F, peaks[0], peaks[1], peaks[2], ncu)
 
     # end to end, host buffer on rank 0 every step (render -> NCCL reduce -> master volume -> D2H, in order), like the
     # N = 1 e2e through synth().  Every rank issues the same collectives whatever happens locally: a local failure

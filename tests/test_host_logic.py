@@ -200,3 +200,56 @@ def test_sharded_render_world2_gloo(luts):
     cases.drive_setup(one, wl)
     ref = one.render(frames, events=wl["events"])
     assert np.max(np.abs(out.astype(np.float64) - ref.astype(np.float64))) <= 1e-5
+
+
+# ---- bench.py: the JSON line at N > 1 (pure dict work) -----------------------------------
+def _bench():
+    import importlib
+    return importlib.import_module("bench")
+
+
+def test_bench_roofline_objects_are_per_launch():
+    b = _bench()
+    V, F = 65536, 8192
+    k_act = 0.725 * V * F                                   # rendered voice-frames of one launch
+    r = b.roofline_objects(k_act, 0.69, V, F, 6446.3, 1965.0, "measured",
+                           {"dram_bytes_read": 18541056, "dram_bytes_write": 125184, "warp_instructions": 399726229})
+    alive = k_act / F
+    algo = alive * b.BYTES_PER_VOICE_LAUNCH + (V - alive) * 32.0 + F * 8
+    assert abs(r["roofline"]["achieved"] - algo / 0.69e-3 / 1e9) < 1e-9
+    assert r["roofline"]["bound"] == "hbm" and r["roofline"]["traffic"] == 18541056 + 125184
+    assert abs(r["roofline"]["frac"] - r["roofline"]["achieved"] / 6446.3) < 1e-12
+    assert 0.2 < r["roofline_fp32"]["frac"] < 0.6 and 15.0 <= r["roofline_fp32"]["flops_per_voice_sample"] <= 32.0
+    assert 0.3 < r["roofline_issue"]["frac"] < 0.8
+    assert b.roofline_objects(k_act, 0.69, V, F, 6446.3, 1965.0, "measured", None)["roofline_issue"] is None
+
+
+def test_bench_weak_headline_swaps_the_job_not_the_contract():
+    b = _bench()
+    V, world, F, steps = 65536, 8, 8192, 5
+    roof = b.roofline_objects(0.7 * V // world * F, 0.45, V // world, F, 6446.3, 1965.0, "measured", None)
+    line = {"metric": b.METRIC, "value": 7.5e11, "unit": b.UNIT, "n_gpus": world, "steps": steps, "warmup": 3,
+            "ms_per_step": 0.52, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": b.WORKLOAD % V, "voices": V, "frames_per_step": F},
+            "e2e": {"value": 6.1e11, "unit": b.UNIT, "h2d_bytes_per_step": 1.0, "d2h_bytes_per_step": 2.0},
+            "gpu_launches": 15, "clocks": None}
+    line.update(roof)
+    # no weak leg / no weak e2e: the strong line is emitted untouched
+    assert b.weak_headline(line, None, V, world, F, steps) is line
+    assert b.weak_headline(line, {"act": 1.0, "ms": 1.0, "launches": 1, "e2e": None}, V, world, F, steps) is line
+    act = 0.725 * V * world * F * steps
+    w_roof = b.roofline_objects(0.725 * V * F, 0.69, V, F, 6446.3, 1965.0, "measured", None)
+    weak = {"act": act, "ms": 0.715 * steps, "launches": 20, "roof": w_roof,
+            "e2e": {"value": 3.4e12, "unit": b.UNIT, "h2d_bytes_per_step": 70000.0, "d2h_bytes_per_step": 65536.0}}
+    out = b.weak_headline(line, weak, V, world, F, steps)
+    assert out is not line and line["scaling"] == "strong"                      # the input is not edited
+    assert out["scaling"] == "weak" and out["n_gpus"] == world and out["metric"] == b.METRIC and out["unit"] == b.UNIT
+    assert abs(out["value"] - act / (0.715 * steps * 1e-3)) < 1.0 and abs(out["ms_per_step"] - 0.715) < 1e-12
+    assert out["e2e"] is weak["e2e"] and out["gpu_launches"] == 20
+    assert out["config"]["voices"] == V * world and out["config"]["voices_per_gpu"] == V
+    assert abs(out["config"]["active_fraction"] - 0.725) < 1e-9
+    assert out["roofline"] is w_roof["roofline"] and out["roofline_fp32"] is w_roof["roofline_fp32"]
+    s = out["strong_scaling"]
+    assert s["value"] == 7.5e11 and s["e2e"] == 6.1e11 and s["voices_total"] == V and s["voices_per_gpu"] == V // world
+    import json
+    assert "\n" not in json.dumps(out)
