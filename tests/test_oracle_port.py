@@ -133,3 +133,31 @@ def test_reference_matches_golden_wav_patch(n, golden_wav_patches, tmp_path):
     gold = golden_wav_patches["p%d_out" % n]
     out, ph, fin = trace_render(s, gold.shape[0])
     assert np.array_equal(out.view(np.uint32), gold.view(np.uint32))
+
+
+def _shipped_patch_ids():
+    import glob
+    import os
+    ref = os.environ.get("SKRED_REF", "/root/reference")
+    return sorted(int(os.path.basename(p)[:-3]) for p in glob.glob(os.path.join(ref, "*.sk")))
+
+
+@needs_ref
+@pytest.mark.skipif(not _shipped_patch_ids(), reason="no skred tree here (the GPU box): the committed fixtures cover 29 patches")
+def test_every_shipped_patch_shim_over_port_equals_reference():
+    """All 64 `.sk` patches of the skred tree (not only the 29 with committed fixtures), read where they lie with their
+    wav files, 0.5 s with the sequencer running: the drop-in shim over the restatement leaves the same mix and the same
+    evolving words as the compiled reference, bit for bit (tools/cpu_all_patches.py 441000 runs the full 10 s of BASELINE
+    configs[0] on each and prints the table: profiles/r01_s8_all_patches_cpu.txt)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import cpu_all_patches as AP
+    ids = _shipped_patch_ids()
+    assert len(ids) >= 60
+    sounding = 0
+    for n in ids:
+        mix, state, peak = AP.run_patch(n, 22050)
+        assert mix and state is True, (n, mix, state)
+        sounding += peak > 0.0
+    assert sounding >= 40
