@@ -3,7 +3,7 @@
 (oracle/skred_port.c behind the engine's C-ABI) against the compiled reference.  It exercises the SAME host code the
 product runs (csrc/synth_shim.c: setters, parameter records, ordered ops, the timestamped event queue) — only the
 engine under the C-ABI is the port instead of the CUDA one (tools/gpu_fuzz_sweep.py / gpu_event_fuzz_sweep.py are the
-GPU twins).   python tools/cpu_fuzz_sweep.py [first_seed] [n_wire] [n_event]"""
+GPU twins).   python tools/cpu_fuzz_sweep.py [first_seed] [n_wire] [n_event] [dense: voices drawn from the first K]"""
 import os
 import sys
 import time
@@ -20,28 +20,27 @@ from oracle import oracle as O  # noqa: E402
 
 
 def upstream_ub_armed(seed):
-    """`C<n>` stores any n: cmod_set does not validate (synth.c:646-650), and a sounding CZ voice then reads
+    """`C<n>` stores any n: cmod_set does not validate (synth.c:646-650), and a rendering CZ voice then reads
     voice_sample[n] (synth.c:263-266) -- past the array for n >= VOICE_MAX, i.e. whatever global the reference's linker
-    put there.  The product reads silence instead (csrc/partition.h skb_live_mods).  Replays the seed's lines and says
-    whether some voice has such an edge live (mode, depth and amplitude non-zero) when the first difference shows."""
+    put there.  The product reads silence instead (csrc/partition.h skb_live_mods).  Replays the seed's lines and
+    returns a description of the first callback in which some voice renders with such an edge live (mode, depth and
+    amplitude non-zero, not finished), or None if the stream never gets there."""
     import numpy as np
     rng = np.random.RandomState(seed)
-    ref, dut = O.RefSkred(SE.V, run_seq=False), O.PortSkred(SE.V, run_seq=False)
+    dut = O.PortSkred(SE.V, run_seq=False)
     for step in range(60):
         for _ in range(rng.randint(1, 12)):
-            ln = SE.rand_line(rng)
-            ref.wire(ln)
-            dut.wire(ln)
+            dut.wire(SE.rand_line(rng))
+        osc, mode = dut.array("voice_cz_mod_osc", SE.I), dut.array("voice_cz_mode", SE.I)
+        depth, amp = dut.array("voice_cz_mod_depth", SE.F), dut.array("voice_amp", SE.F)
+        fin = dut.array("voice_finished", SE.I)
+        hit = [int(v) for v in range(SE.V)
+               if osc[v] >= SE.V and mode[v] != 0 and depth[v] != 0.0 and amp[v] != 0.0 and fin[v] == 0]
+        if hit:
+            return "from step %d on voice(s) %s render with cz_mode != 0 and cz_mod_osc %s >= VOICE_MAX" % (
+                step, hit, [int(osc[v]) for v in hit])
         n = int(rng.choice([512, 512, 512, 64, 300]))
-        oa, ob = ref.render(n, block=n), dut.render(n, block=n)
-        if not np.array_equal(oa.view(np.uint32), ob.view(np.uint32)):
-            osc, mode = dut.array("voice_cz_mod_osc", SE.I), dut.array("voice_cz_mode", SE.I)
-            depth, amp = dut.array("voice_cz_mod_depth", SE.F), dut.array("voice_amp", SE.F)
-            hit = [int(v) for v in range(SE.V) if osc[v] >= SE.V and mode[v] != 0 and depth[v] != 0.0 and amp[v] != 0.0]
-            if hit:
-                return "step %d: voice(s) %s sound with cz_mode != 0 and cz_mod_osc %s >= VOICE_MAX" % (
-                    step, hit, [int(osc[v]) for v in hit])
-            return None
+        dut.render(n, block=n)
     return None
 
 
@@ -49,6 +48,19 @@ def main():
     first = int(sys.argv[1]) if len(sys.argv) > 1 else 100
     n_wire = int(sys.argv[2]) if len(sys.argv) > 2 else 100
     n_event = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+    dense = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+    if dense:
+        # skode streams whose lines pick their voices (targets of `v`, modulators, links, copies) among the first
+        # `dense` voices only: long chains of interacting setters on few voices instead of 64 nearly independent ones
+        plain = SE.rand_line
+
+        def dense_line(rng):
+            SE.V = dense
+            try:
+                return plain(rng)
+            finally:
+                SE.V = 64
+        SE.rand_line = dense_line
     luts = cases.load_luts()
     bad = []
     t0 = time.time()
@@ -63,8 +75,9 @@ def main():
             else:
                 bad.append(("wire", seed, traceback.format_exc(limit=2)))
     t1 = time.time()
-    print("random skode streams (every array of synth.def word for word after each callback): seeds %d..%d, %d failed, %.0f s"
-          % (first, first + n_wire - 1, sum(1 for b in bad if b[0] == "wire"), t1 - t0), flush=True)
+    print("random skode streams%s (every array of synth.def word for word after each callback): seeds %d..%d, %d failed, %.0f s"
+          % (" on the first %d voices" % dense if dense else "", first, first + n_wire - 1,
+             sum(1 for b in bad if b[0] == "wire"), t1 - t0), flush=True)
     for seed, armed in ub:
         print("  seed %d not comparable: upstream undefined behaviour reached -- %s" % (seed, armed), flush=True)
     calls = [512, 1536, 4096, 8192]
