@@ -13,7 +13,10 @@ block boundaries.  One STEP = one batch of `--frames` frames
 
   value   device-resident: params/state/tables/pending events live in HBM; K steps of
           skb_shim_render_mix (+ NCCL reduce of the stereo partial mixes for N > 1),
-          CUDA events on the launching stream, max over ranks.
+          CUDA events on the launching stream, max over ranks.  N = 1: the L2 is flushed before
+          every timed step (256 MB fill outside the per-step events); the K steps back to back
+          are config.value_l2_unflushed.  N > 1: not flushed (18 MB of records per GPU and launch,
+          each word touched once; N = 1 measures flushed = unflushed within 1 %).
   e2e     the call a skred host makes: synth(buffer, NULL, frames, 2, NULL) with a HOST
           buffer — event firing, parameter/op/trace H2D, kernels, D2H of the block
           inside the timed region (N > 1: render_mix -> reduce -> finish on rank 0).
@@ -256,7 +259,8 @@ def own_arm(a):
     hbm_peak, sm_mhz, peak_kind = load_peaks()
 
     sk = Skred(V, device=local, rank=rank, world=world, max_frames=max(F, 512))
-    total_frames = (a.warmup + a.steps) * F * 2 + 4 * F
+    # steps this arm renders: W + K device-resident, 3 kernel-alone, K with the L2 flushed, W + K end to end
+    total_frames = (2 * a.warmup + 3 * a.steps + 8) * F
     wl = W.config5(V, seconds=600.0, luts=load_luts(), event_seconds=total_frames / SR + 1.0, stationary=True)
     W.install(sk, wl)
     ev = W.to_skb_events(wl["timed"])
@@ -387,7 +391,7 @@ def own_arm(a):
         junk = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
         pairs = []
         a_f = sk.stats().active_voice_frames
-        for _ in range(min(a.steps, 5)):
+        for _ in range(a.steps):
             junk.fill_(1)
             f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             f0.record(stream)
@@ -487,6 +491,8 @@ def own_arm(a):
             line["block_latency_ms_p50_64_voices"] = block_latency_small(local, a.latency_blocks)
         if world == 1 and not a.no_cpu:
             line["cpu_baseline"] = cpu_baseline(V)
+        if world == 1:
+            line = l2_flushed_headline(line, flushed_act, flushed_ms, a.steps, V, F)
         emit(weak_headline(line, weak, V, world, F, a.steps))
     if world > 1:
         dist.barrier()
@@ -525,6 +531,28 @@ def roofline_objects(k_act, k_ms, owned, F, hbm_peak, sm_mhz, peak_kind, ncu):
             "warp_instructions_per_launch": ncu["warp_instructions"],
             "note": "instruction count from the committed ncu capture of this command (profiles/r01_ncu_counters.json), duration measured live"},
     }
+
+
+def l2_flushed_headline(line, flushed_act, flushed_ms, steps, V, F):
+    """N = 1: the headline `value` / `ms_per_step` are the K steps timed with the L2 flushed before each one (a 256 MB
+    fill, larger than the 126 MB L2, outside the per-step CUDA events); the same K steps back to back without the flush
+    stay in the line as config.value_l2_unflushed.  Pure dict work (tested on CPU)."""
+    if not flushed_ms or flushed_ms <= 0.0:
+        return line
+    out = dict(line)
+    cfg = dict(line["config"])
+    cfg.pop("value_l2_flushed", None)
+    cfg["value_l2_unflushed"] = line["value"]
+    cfg["ms_per_step_l2_unflushed"] = line["ms_per_step"]
+    cfg["l2"] = ("flushed before every timed step: a 256 MB fill (the L2 holds 126 MB) outside the per-step CUDA events; "
+                 "state+params are %.1f MB per launch, each word touched once per launch (the path is issue bound, DRAM < 1 %% "
+                 "of peak: value_l2_unflushed is the same K steps back to back)" % (V * 276 / 1e6))
+    cfg["active_fraction"] = flushed_act / (float(V) * F * steps)
+    cfg["value_counting_all_voice_slots"] = float(V) * F * steps / (flushed_ms * 1e-3)
+    out["config"] = cfg
+    out["value"] = flushed_act / (flushed_ms * 1e-3)
+    out["ms_per_step"] = flushed_ms / steps
+    return out
 
 
 def weak_headline(line, weak, V, world, F, steps):

@@ -253,3 +253,19 @@ def test_bench_weak_headline_swaps_the_job_not_the_contract():
     assert s["value"] == 7.5e11 and s["e2e"] == 6.1e11 and s["voices_total"] == V and s["voices_per_gpu"] == V // world
     import json
     assert "\n" not in json.dumps(out)
+
+
+def test_bench_l2_flushed_headline():
+    b = _bench()
+    V, F, steps = 65536, 8192, 20
+    line = {"value": 5.5e11, "ms_per_step": 0.70, "scaling": "weak",
+            "config": {"voices": V, "l2": "x", "value_l2_flushed": 5.4e11, "active_fraction": 0.72,
+                       "value_counting_all_voice_slots": 7.6e11}}
+    assert b.l2_flushed_headline(line, 0.0, None, steps, V, F) is line          # no flushed loop (N > 1): untouched
+    act, ms = 0.725 * V * F * steps, 0.71 * steps
+    out = b.l2_flushed_headline(line, act, ms, steps, V, F)
+    assert out is not line and line["value"] == 5.5e11
+    assert abs(out["value"] - act / (ms * 1e-3)) < 1.0 and abs(out["ms_per_step"] - 0.71) < 1e-12
+    assert out["config"]["value_l2_unflushed"] == 5.5e11 and out["config"]["ms_per_step_l2_unflushed"] == 0.70
+    assert "value_l2_flushed" not in out["config"] and out["config"]["l2"].startswith("flushed before every timed step")
+    assert abs(out["config"]["active_fraction"] - 0.725) < 1e-12
