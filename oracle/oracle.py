@@ -13,6 +13,7 @@ lines or synth.h setter calls, then `synth(); seq();` callbacks of 512 frames.
 """
 import ctypes as C
 import os
+import shutil
 import sys
 
 import numpy as np
@@ -41,7 +42,10 @@ class HarnessSkred(SynthAPI):
     def __init__(self, path, voice_max, run_seq=True):
         if not os.path.exists(path):
             raise FileNotFoundError("%s missing: run `python oracle/build_oracle.py --voices %d`" % (path, voice_max))
-        lib = C.CDLL(private_copy(path))
+        copy = private_copy(path)
+        lib = C.CDLL(copy)
+        # the mapping outlives the file: without this every instance of a sweep leaves a 3 MB copy in /tmp
+        shutil.rmtree(os.path.dirname(copy), ignore_errors=True)
         super().__init__(lib, voice_max)
         assert lib.ref_voice_max() == voice_max
         lib.ref_render.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int]
