@@ -492,7 +492,10 @@ def own_arm(a):
         if world == 1 and not a.no_cpu:
             line["cpu_baseline"] = cpu_baseline(V)
         if world == 1:
-            line = l2_flushed_headline(line, flushed_act, flushed_ms, a.steps, V, F)
+            try:
+                line = l2_flushed_headline(line, flushed_act, flushed_ms, a.steps, V, F)
+            except Exception as exc:                     # (the unflushed line is complete on its own)
+                sys.stderr.write("bench.py: flushed headline not applied: %r\n" % (exc,))
         emit(weak_headline(line, weak, V, world, F, a.steps))
     if world > 1:
         dist.barrier()
