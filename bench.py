@@ -23,11 +23,20 @@ block boundaries.  One STEP = one batch of `--frames` frames
   cpu_baseline  the compiled reference (oracle/_ref) on ONE host core over a bounded
           sample (first 4096 voices of the same load).
 
-N > 1 (`scaling`: "weak", SURVEY §8e — voices shard with one exchange step): every GPU
-renders a full V-voice job, rank r holding voices r*V ... of an N*V-voice render, partial
-mixes summed to rank 0 by an NCCL reduce (value: overlapped with the next render; e2e: in
-order, host buffer out of rank 0 every step).  The ONE V-voice job cut N ways (BASELINE
-configs[4] as written) is measured in the same run and reported as `strong_scaling`.
+N > 1 (`scaling`: "strong"): BASELINE configs[4] as written — ONE V-voice job, voice-sharded
+over the N GPUs (whole modulation groups per GPU, csrc/partition.h), the stereo partial mixes
+summed to rank 0 by the engine's exchange step behind the C-ABI (skb_reduce_mix: ncclReduce
+over NVLink; value: overlapped with the next render on a second stream; e2e: render -> reduce
+-> master volume -> host buffer out of rank 0, in order, every step).  The companion job with
+the per-GPU work fixed (every GPU renders V voices of an N*V-voice render) rides in the same
+line as `weak_scaling`; BASELINE names no such config, so it is never the headline.
+
+`roofline` is the BINDING bound of the dominant kernel: individually rounded fp32
+ops per rendered voice-sample against 148 SMs x 128 lanes x SM clock, duration measured live
+with the engine's CUDA events.  The HBM figure the contract template asks for is `roofline_hbm`
+(0.3 % of peak: not the bound).  `roofline.traffic` / `roofline_issue` use ncu counters of one
+launch of this workload, and only when profiles/r02_ncu_counters.json was captured from the
+kernel sources of this very tree (a hash of csrc/ is checked); otherwise they are null.
 
 `--impl reference` times the reference's own synth.c (oracle/_ref, pinned flags)
 voice-sharded over ALL host cores (independent processes — the reference is
@@ -91,11 +100,31 @@ def emit(line):
     os.write(_JSON_FD if _JSON_FD is not None else 1, data)
 
 
-def load_ncu_counters():
-    """Per-launch counters of the dominant kernel from the committed ncu capture of this same command
-    (profiles/): DRAM bytes for roofline.traffic, warp instructions for the issue-slot roofline."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_counters.json")
-    return json.load(open(p)) if os.path.exists(p) else None
+def kernel_source_hash():
+    """sha256 over the engine's kernel sources: what an ncu capture must have been taken from to describe this build."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "skred_b200", "csrc")
+    for f in ("engine.cu", "voice_kernels.cuh", "free_kernel.cuh", "partition.h"):
+        with open(os.path.join(d, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def load_ncu_counters(path=None):
+    """Per-launch counters of the dominant kernel (DRAM bytes for roofline.traffic, warp instructions for the
+    issue-slot roofline) from one `ncu --set full` capture of THIS workload, written by tools/ncu_counters.py
+    together with the hash of the kernel sources it was taken from.  A capture of other sources is STALE: it is
+    refused (None) and the reason is reported in the line instead of a number that no longer describes the kernel."""
+    p = path or os.path.join(ROOT, "profiles", "r02_ncu_counters.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    if d.get("src_hash") != kernel_source_hash():
+        sys.stderr.write("bench.py: %s was captured from other kernel sources (%s != %s): traffic / issue counters not reported\n"
+                         % (os.path.basename(p), d.get("src_hash"), kernel_source_hash()))
+        return None
+    return d
 
 
 def load_luts():
@@ -246,6 +275,7 @@ def own_arm(a):
     import torch.distributed as dist
     from skred_b200 import Skred
     from skred_b200.host import load_engine_lib
+    from skred_b200.sharded import comm_init
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -259,8 +289,9 @@ def own_arm(a):
     hbm_peak, sm_mhz, peak_kind = load_peaks()
 
     sk = Skred(V, device=local, rank=rank, world=world, max_frames=max(F, 512))
-    # steps this arm renders: W + K device-resident, 3 kernel-alone, K with the L2 flushed, W + K end to end
-    total_frames = (2 * a.warmup + 3 * a.steps + 8) * F
+    # steps this arm renders: (W + R*K) device-resident, 3 kernel-alone, K with the L2 flushed, W + K end to end, latency blocks
+    reps_guess = max(1, min(40, int(np.ceil(a.min_timed_s / max(a.steps * 0.7e-3 * F / 8192.0, 1e-6))))) if a.min_timed_s > 0 else 1
+    total_frames = (2 * a.warmup + (2 * reps_guess + 4) * a.steps + 8) * F + (a.latency_blocks + 64) * 512
     wl = W.config5(V, seconds=600.0, luts=load_luts(), event_seconds=total_frames / SR + 1.0, stationary=True)
     W.install(sk, wl)
     ev = W.to_skb_events(wl["timed"])
@@ -272,13 +303,17 @@ def own_arm(a):
     owned = st0.n_owned_voices if world > 1 else V
 
     # a real stream: the legacy default stream's handle is 0, which the engine reads as "use your own",
-    # and then neither the CUDA events below nor NCCL would be ordered with the kernels
+    # and then neither the CUDA events below nor the exchange step would be ordered with the kernels
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     sp = C.c_void_p(stream.cuda_stream)
     assert sp.value
     d_mix = torch.zeros((F, 2), dtype=torch.float32, device="cuda")
     out = np.zeros((F, 2), dtype=np.float32)
+    if world > 1:
+        # the exchange step behind the C-ABI: skb_comm_init_rank (ncclCommInitRank) + skb_reduce_mix (ncclReduce);
+        # torch.distributed ships the 128-byte id and times / synchronises the ranks
+        comm_init(sk, dist, eng)
 
     LF = a.launch_frames                     # frames per launch: events land on 512-frame boundaries
     mix_ptr = d_mix.data_ptr()
@@ -292,14 +327,19 @@ def own_arm(a):
         if r != 0:
             raise RuntimeError("render failed %d" % r)
 
+    def reduce_mix(ptr, n, stream_ptr):
+        r = eng.skb_reduce_mix(sk.engine, ptr, n, stream_ptr)
+        if r != 0:
+            raise RuntimeError("skb_reduce_mix failed %d: %s" % (r, eng.skb_error_string(sk.engine).decode()))
+
     def render_step():
         render_calls(mix_ptr)
 
-    # N > 1, device-resident loop: the NCCL reduce of step k runs on its own stream while the engine renders
+    # N > 1, device-resident loop: the reduce of step k runs on its own stream while the engine renders
     # step k + 1 into the other mix buffer (a batch render has no reason to serialise them)
     comm = torch.cuda.Stream() if world > 1 else None
+    cp = C.c_void_p(comm.cuda_stream) if world > 1 else None
     d_mix2 = [d_mix, torch.zeros_like(d_mix)] if world > 1 else [d_mix]
-    rendered = [torch.cuda.Event() for _ in d_mix2]
     reduced = [torch.cuda.Event() for _ in d_mix2]
     step_no = [0]
 
@@ -311,24 +351,23 @@ def own_arm(a):
         step_no[0] += 1
         stream.wait_event(reduced[k])                     # the reduce that last read this buffer is done
         render_calls(d_mix2[k].data_ptr())
-        rendered[k].record(stream)
-        with torch.cuda.stream(comm):
-            comm.wait_event(rendered[k])
-            dist.reduce(d_mix2[k], dst=0, op=dist.ReduceOp.SUM)
-            reduced[k].record(comm)
+        reduce_mix(d_mix2[k].data_ptr(), F, cp)           # ordered after the render by an event inside the engine
+        reduced[k].record(comm)
 
     def drain_device():
         if world > 1:
             stream.wait_stream(comm)
 
-    def step_e2e():
+    def step_e2e(n=F, buf=out):
         if world == 1:
-            sk.lib.synth(out.ctypes.data, None, F, 2, None)
+            sk.lib.synth(buf.ctypes.data, None, n, 2, None)
         else:
-            render_step()
-            dist.reduce(d_mix, dst=0, op=dist.ReduceOp.SUM)
+            r = sk.lib.skb_shim_render_calls(min(LF, n), max(1, n // LF), mix_ptr, sp)
+            if r != 0:
+                raise RuntimeError("render failed %d" % r)
+            reduce_mix(mix_ptr, n, sp)
             if rank == 0:
-                sk.finish(mix_ptr, F, out, sp)
+                sk.finish(mix_ptr, n, buf, sp)
             else:
                 sk.lib.skb_shim_discard_gain()
                 eng.skb_sync(sk.engine, sp)
@@ -345,6 +384,13 @@ def own_arm(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def sum_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     # ---- device-resident value ------------------------------------------------
     for _ in range(a.warmup):
         step_device()
@@ -354,24 +400,43 @@ def own_arm(a):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    eng.skb_sync(sk.engine, sp)
-    s_before = sk.stats()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kern_ms = []
-    e0.record(stream)
-    for _ in range(a.steps):
-        step_device()
-        sk.lib.skb_shim_discard_gain()
-    drain_device()
-    e1.record(stream)
-    barrier()
-    dev_ms = max_over_ranks(e0.elapsed_time(e1))
-    eng.skb_sync(sk.engine, sp)
-    s_after = sk.stats()
-    launches = int(s_after.kernel_launches - s_before.kernel_launches) + (a.steps if world > 1 else 0)
+
+    def timed_k_steps():
+        """EXACTLY K steps between a barrier + synchronize on both sides; returns (device ms max over ranks, rendered
+        voice-frames over all ranks, rank 0's kernel launches)."""
+        barrier()
+        eng.skb_sync(sk.engine, sp)
+        s_b = sk.stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(a.steps):
+            step_device()
+            sk.lib.skb_shim_discard_gain()
+        drain_device()
+        e1.record(stream)
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        eng.skb_sync(sk.engine, sp)
+        s_a = sk.stats()
+        return ms, sum_over_ranks(s_a.active_voice_frames - s_b.active_voice_frames), int(s_a.kernel_launches - s_b.kernel_launches)
+
+    # The K steps are timed R times (each repetition EXACTLY K steps, bracketed as above) until >= --min-timed-s of
+    # device time has been measured (K = 20 steps are 14 ms: too short to be robust on its own); the line reports the
+    # MEDIAN repetition and the spread of all of them.
+    reps = []
+    while True:
+        reps.append(timed_k_steps())
+        spent = sum(r[0] for r in reps) * 1e-3
+        if world > 1:
+            spent = max_over_ranks(spent)                 # every rank must take the same decision
+        if spent >= a.min_timed_s or len(reps) >= reps_guess + 1 or len(reps) >= 40:
+            break
+    order = sorted(range(len(reps)), key=lambda i: reps[i][0])
+    dev_ms, act_dev, launches = reps[order[len(order) // 2]]
+    rep_ms_per_step = [r[0] / a.steps for r in reps]
 
     # dominant kernel alone (k_render_free + bins + reduce), CUDA events inside the engine
-    kern_active = []
+    kern_ms, kern_active = [], []
     for _ in range(3):
         a_b = sk.stats().active_voice_frames
         step_device()
@@ -389,20 +454,23 @@ def own_arm(a):
     flushed_ms, flushed_act = None, 0.0
     if world == 1:
         junk = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-        pairs = []
-        a_f = sk.stats().active_voice_frames
-        for _ in range(a.steps):
-            junk.fill_(1)
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record(stream)
-            step_device()
-            sk.lib.skb_shim_discard_gain()
-            f1.record(stream)
-            pairs.append((f0, f1))
-        torch.cuda.synchronize()
-        eng.skb_sync(sk.engine, sp)
-        flushed_ms = sum(x.elapsed_time(y) for x, y in pairs)
-        flushed_act = float(sk.stats().active_voice_frames - a_f)
+        fl = []
+        for _ in range(len(reps)):                        # as many repetitions of EXACTLY K steps as the loop above
+            pairs = []
+            a_f = sk.stats().active_voice_frames
+            for _ in range(a.steps):
+                junk.fill_(1)
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record(stream)
+                step_device()
+                sk.lib.skb_shim_discard_gain()
+                f1.record(stream)
+                pairs.append((f0, f1))
+            torch.cuda.synchronize()
+            eng.skb_sync(sk.engine, sp)
+            fl.append((sum(x.elapsed_time(y) for x, y in pairs), float(sk.stats().active_voice_frames - a_f)))
+        fl.sort()
+        flushed_ms, flushed_act = fl[len(fl) // 2]       # the median repetition
         del junk
 
     # ---- end to end through synth() ---------------------------------------------
@@ -424,31 +492,40 @@ def own_arm(a):
     eng_us = [(x - y) / a.steps for x, y in zip(sk.stats().host_us, s_b.host_us)]
     eng.skb_sync(sk.engine, sp)
     s_a = sk.stats()
-    ops = int(s_a.ops_applied - s_b.ops_applied)
-    par = int(s_a.params_uploaded - s_b.params_uploaded)
     # counted by the engine from the copies it issues (skb_stats.h2d_bytes / d2h_bytes): parameter records, the
     # per-launch staging block (window list, op lists, wake bits), gain trace; stereo block + counters back
     h2d = (s_a.h2d_bytes - s_b.h2d_bytes) / a.steps
     d2h = (s_a.d2h_bytes - s_b.d2h_bytes) / a.steps
 
-    def sum_over_ranks(x):
-        if world == 1:
-            return float(x)
-        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
     # rendered voice-frames (voices the loop skips — finished one-shots — do not count)
-    act_dev = sum_over_ranks(s_after.active_voice_frames - s_before.active_voice_frames)
     act_e2e = sum_over_ranks(s_a.active_voice_frames - s_b.active_voice_frames)
     value = act_dev / (dev_ms * 1e-3)
     e2e = act_e2e / e2e_s
     k_ms = float(np.mean(kern_ms))
     k_act = float(np.mean(kern_active))
-    ncu = load_ncu_counters() if (V == 65536 and world == 1) else None
-    if ncu and ncu.get("frames", 4096) != F:
-        ncu = None
+    ncu = load_ncu_counters()
+    if ncu and (ncu.get("frames") != F or ncu.get("voices_on_gpu") != owned):
+        ncu = None                                        # counters of another launch shape
     roof = roofline_objects(k_act, k_ms, owned, F, hbm_peak, sm_mhz, peak_kind, ncu)
+
+    # p50 host-observed latency of ONE 512-frame block through the same path (N > 1: every rank renders its shard of
+    # the block, the exchange step, master volume + D2H on rank 0; timed on rank 0 between two host returns)
+    lat = None
+    if not a.no_latency:
+        if world == 1:
+            lat = block_latency(sk, a.latency_blocks)
+        else:
+            blk = np.zeros((512, 2), dtype=np.float32)
+            ts = []
+            for _ in range(20):
+                step_e2e(512, blk)
+            barrier()
+            for _ in range(a.latency_blocks):
+                t0 = time.perf_counter()
+                step_e2e(512, blk)
+                ts.append(time.perf_counter() - t0)
+            barrier()
+            lat = float(np.median(ts) * 1e3)              # rank 0's is reported (the host that gets the buffer)
 
     weak = None
     if world > 1 and not a.no_weak:
@@ -459,53 +536,62 @@ def own_arm(a):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dev_ms / a.steps, "higher_is_better": True,
-            # N = 1 is the first point of the weak-scaling series (V voices per GPU); at N > 1 this line is the ONE-job
-            # (strong) leg and weak_headline() below swaps the N x V-voice job in
-            "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
+            # BASELINE configs[4] as written: ONE V-voice job.  N = 1 renders all of it; N > 1 cuts the same job N ways.
+            "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD % V,
-                       "voices": V, "frames_per_step": F, "frames_per_call": LF, "frames_per_launch": F, "block_frames": 512,
+                       "voices": V, "voices_per_gpu": owned, "frames_per_step": F, "frames_per_call": LF, "frames_per_launch": F,
+                       "block_frames": 512,
                        "active_fraction": act_dev / (V * F * a.steps),
                        "counting": "rendered voice-frames only: voices skipped by synth.c:531-542 (finished one-shots) do not count",
                        "value_counting_all_voice_slots": V * F * a.steps / (dev_ms * 1e-3),
-                       "parallelism": ("voice-sharded x%d, NCCL reduce of stereo partials (value: the reduce of step k overlaps the render "
-                                       "of step k + 1 on a second stream; e2e: render -> reduce -> finish in order)" % world) if world > 1 else "1 GPU",
+                       "timed": "EXACTLY %d steps between barrier + synchronize, repeated %d times (%.3f s of device time in all); "
+                                "value = the median repetition" % (a.steps, len(reps), sum(r[0] for r in reps) * 1e-3),
+                       "ms_per_step_repetitions": {"n": len(reps), "min": min(rep_ms_per_step), "median": dev_ms / a.steps,
+                                                   "max": max(rep_ms_per_step)},
+                       "parallelism": ("ONE %d-voice job voice-sharded x%d (whole modulation groups per GPU), stereo partial mixes summed "
+                                       "to rank 0 by skb_reduce_mix = ncclReduce over NVLink behind the C-ABI (value: the reduce of "
+                                       "step k overlaps the render of step k + 1 on a second stream; e2e: render -> reduce -> master "
+                                       "volume -> host buffer, in order)" % (V, world)) if world > 1 else "1 GPU",
                        "launches": "the engine renders the %d callbacks of a step in one launch; events are applied in-kernel at the 512-frame boundaries" % (F // LF),
                        "l2": "state+params %.1f MB per launch, each word touched once per launch; not flushed between the timed steps "
                              "(the path is issue bound, DRAM < 1 %% of peak) -- value_l2_flushed is the same loop with a 256 MB fill "
                              "before every step, timed per step" % (owned * 276 / 1e6),
                        "value_l2_flushed": (flushed_act / (flushed_ms * 1e-3)) if flushed_ms else None},
-            "roofline": roof["roofline"], "roofline_fp32": roof["roofline_fp32"], "roofline_issue": roof["roofline_issue"],
+            "roofline": roof["roofline"], "roofline_hbm": roof["roofline_hbm"], "roofline_issue": roof["roofline_issue"],
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_s / a.steps * 1e3, "api": "synth(buffer, NULL, %d, 2, NULL)" % F,
+                    "ms_per_step": e2e_s / a.steps * 1e3,
+                    "api": ("synth(buffer, NULL, %d, 2, NULL)" % F) if world == 1 else
+                           ("per rank: %d x skb_shim_render_mix(%d) -> skb_reduce_mix -> rank 0: skb_shim_finish into a host buffer" % (F // LF, LF)),
                     "host_ms_per_step": None if world > 1 else {"flush_and_traces": host_ms[0], "queue_segments": host_ms[1],
                                                                 "fire_events": host_ms[2], "finish_launch_kernels_d2h_sync": host_ms[3],
                                                                 "of_which_launch_host": eng_us[0] * 1e-3, "finish_enqueue": eng_us[1] * 1e-3,
                                                                 "stream_wait": eng_us[2] * 1e-3}},
-            "gpu_launches": launches,
+            "gpu_launches": launches + (a.steps if world > 1 else 0),
             "clocks": clk,
-            "block_latency_ms_p50": None,
+            "block_latency_ms_p50": lat,
         }
         if world == 1 and not a.no_latency:
-            line["block_latency_ms_p50"] = block_latency(sk, a.latency_blocks)
             line["block_latency_ms_p50_64_voices"] = block_latency_small(local, a.latency_blocks)
-        if world == 1 and not a.no_cpu:
-            line["cpu_baseline"] = cpu_baseline(V)
+        if not a.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(V)          # rank 0's host, one core, a bounded sample — at every N
         if world == 1:
             try:
                 line = l2_flushed_headline(line, flushed_act, flushed_ms, a.steps, V, F)
             except Exception as exc:                     # (the unflushed line is complete on its own)
                 sys.stderr.write("bench.py: flushed headline not applied: %r\n" % (exc,))
-        emit(weak_headline(line, weak, V, world, F, a.steps))
+        emit(weak_companion(line, weak, V, world, F, a.steps))
     if world > 1:
         dist.barrier()
+        eng.skb_comm_destroy(sk.engine)
         dist.destroy_process_group()
     return 0
 
 
 def roofline_objects(k_act, k_ms, owned, F, hbm_peak, sm_mhz, peak_kind, ncu):
-    """roofline / roofline_fp32 / roofline_issue of one launch of the dominant kernel on ONE GPU: k_act rendered
-    voice-frames in k_ms (the engine's CUDA events around k_render_free + bins + reduce), `owned` voices on that GPU."""
+    """roofline (binding: fp32 issue) / roofline_hbm / roofline_issue of one launch of the dominant kernel on ONE GPU:
+    k_act rendered voice-frames in k_ms (the engine's CUDA events around k_render_free + bins + reduce, measured live),
+    `owned` voices on that GPU.  `roofline_fp32` is kept as an alias of `roofline` for readers of round 1's lines."""
     # launch traffic: every owned voice's amp + first state group are read (32 B) to decide the skip;
     # a rendered voice moves its full 276 B record
     alive_per_launch = k_act / F
@@ -519,20 +605,26 @@ def roofline_objects(k_act, k_ms, owned, F, hbm_peak, sm_mhz, peak_kind, ncu):
     ach_flops = k_act * flops_vs / (k_ms * 1e-3)
     traffic = float(ncu["dram_bytes_read"] + ncu["dram_bytes_write"]) if ncu else None
     issue_peak = N_SM * 4 * sm_mhz * 1e6                     # warp instructions per second: 4 schedulers per SM
+    fp32 = {"bound": "fp32-issue", "achieved": ach_flops / 1e12, "peak": fp32_peak / 1e12, "unit": "TFLOP/s",
+            "frac": ach_flops / fp32_peak, "traffic": traffic, "peak_kind": "%d SMs x %d fp32 lanes x %.0f MHz (%s sm_max_mhz); "
+            "no FMA: parity mode rounds every op, 1 op = 1 lane-issue" % (N_SM, FP32_LANES_PER_SM, sm_mhz, peak_kind),
+            "flops_per_voice_sample": flops_vs, "flops_per_launch": k_act * flops_vs,
+            "kernel": "k_render_free(+k_render_bins,+k_reduce_rows)", "kernel_ms": k_ms,
+            "note": "SURVEY 8d: the path is FP32-issue bound (HBM: roofline_hbm); ops counted from synth.c per class, "
+                    "duration = the engine's CUDA events around the launch, measured in this run"}
     return {
-        "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                     "traffic": traffic, "peak_kind": peak_kind, "kernel": "k_render_free(+k_render_bins,+k_reduce_rows)",
-                     "kernel_ms": k_ms,
-                     "note": "the path is FP32-issue bound, not HBM bound (SURVEY 8d): see roofline_fp32"},
-        "roofline_fp32": {"bound": "fp32-issue (no FMA: parity mode rounds every op)", "achieved": ach_flops / 1e12,
-                          "peak": fp32_peak / 1e12, "unit": "Tflop/s (1 op per lane-issue)",
-                          "frac": ach_flops / fp32_peak, "flops_per_voice_sample": flops_vs},
+        "roofline": fp32,
+        "roofline_fp32": fp32,
+        "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                         "traffic": traffic, "peak_kind": peak_kind, "algorithmic_bytes_per_launch": algo_bytes,
+                         "kernel_ms": k_ms, "note": "not the bound: state is register-resident for a whole launch"},
         "roofline_issue": None if not ncu else {
             "bound": "warp-instruction issue slots (4 schedulers x %d SMs x SM clock)" % N_SM,
             "achieved": ncu["warp_instructions"] / (k_ms * 1e-3) / 1e12, "peak": issue_peak / 1e12,
             "unit": "T warp-instructions/s", "frac": ncu["warp_instructions"] / (k_ms * 1e-3) / issue_peak,
             "warp_instructions_per_launch": ncu["warp_instructions"],
-            "note": "instruction count from the committed ncu capture of this command (profiles/r01_ncu_counters.json), duration measured live"},
+            "note": "instruction count from the ncu capture of this workload on these kernel sources (src_hash %s), duration measured live"
+                    % ncu.get("src_hash")},
     }
 
 
@@ -558,75 +650,66 @@ def l2_flushed_headline(line, flushed_act, flushed_ms, steps, V, F):
     return out
 
 
-def weak_headline(line, weak, V, world, F, steps):
-    """N > 1: make the weak-scaling job (every GPU renders a full V-voice job, an N x V-voice render; SURVEY 8e: voices
-    shard with one exchange step) the headline of the JSON line and keep the strong-scaling job (ONE V-voice job cut N
-    ways, BASELINE configs[4] as written) beside it as `strong_scaling`.  Pure dict work (tested on CPU).  Falls back
-    to the strong headline when the weak leg has no end-to-end number: `value` and `e2e` must be the same job."""
-    if not weak or not weak.get("e2e"):
+def weak_companion(line, weak, V, world, F, steps):
+    """N > 1: the headline stays BASELINE configs[4] as written (ONE V-voice job cut N ways, `scaling`: "strong");
+    the job with the per-GPU work fixed (every GPU renders a full V-voice job, an N x V-voice render) is attached
+    as `weak_scaling`.  Pure dict work (tested on CPU)."""
+    if not weak:
         return line
     out = dict(line)
-    w_value = weak["act"] / (weak["ms"] * 1e-3)
-    out["strong_scaling"] = {
-        "value": line["value"], "unit": line["unit"], "ms_per_step": line["ms_per_step"], "e2e": line["e2e"]["value"],
-        "voices_total": V, "voices_per_gpu": V // world, "gpu_launches": line["gpu_launches"],
-        "kernel_ms": line["roofline"]["kernel_ms"],
-        "note": "ONE %d-voice job (BASELINE configs[4] as written) cut %d ways, same loop: a launch cannot be shorter than its "
-                "slowest voice's sequential frames, so a fixed job this small stops scaling at 2 GPUs (DESIGN.md 6)" % (V, world)}
-    out.update(value=w_value, ms_per_step=weak["ms"] / steps, scaling="weak", e2e=weak["e2e"], gpu_launches=weak["launches"])
-    cfg = dict(line["config"])
-    cfg.update(workload="%d x (%s): rank r renders voices r*%d ... of an %d-voice render" % (world, cfg["workload"], V, V * world),
-               voices=V * world, voices_per_gpu=V,
-               active_fraction=weak["act"] / (float(V) * world * F * steps),
-               value_counting_all_voice_slots=float(V) * world * F * steps / (weak["ms"] * 1e-3),
-               l2="state+params %.1f MB per launch and GPU, each word touched once per launch; not flushed between the timed "
-                  "steps (the path is issue bound, DRAM < 1 %% of peak; N = 1 reports value_l2_flushed)" % (V * 276 / 1e6),
-               parallelism="%d GPUs x %d voices each (per-GPU work fixed), NCCL reduce of stereo partials to rank 0 (value: the "
-                           "reduce of step k overlaps the render of step k + 1 on a second stream; e2e: render -> reduce -> "
-                           "finish -> host buffer in order)" % (world, V))
-    out["config"] = cfg
+    w = {"value": weak["act"] / (weak["ms"] * 1e-3), "unit": line["unit"], "ms_per_step": weak["ms"] / weak.get("steps", steps),
+         "steps": weak.get("steps", steps), "voices_total": V * world, "voices_per_gpu": V,
+         "e2e": weak["e2e"]["value"] if weak.get("e2e") else None,
+         "e2e_ms_per_step": weak["e2e"].get("ms_per_step") if weak.get("e2e") else None,
+         "gpu_launches": weak["launches"],
+         "active_fraction": weak["act"] / (float(V) * world * F * weak.get("steps", steps)),
+         "note": "not a BASELINE config: %d GPUs x %d voices each (rank r renders voices r*%d ... of a %d-voice render), "
+                 "the same exchange step; reported to show the path scales with the voices a box is given" % (world, V, V, V * world)}
     if weak.get("roof"):
-        out.update(weak["roof"])
-    out.pop("weak_scaling", None)
+        w["roofline"] = weak["roof"]["roofline"]
+    out["weak_scaling"] = w
     return out
 
 
 def weak_scaling_leg(a, local, world, stream, sp, peaks):
-    """N > 1 only, reported beside the strong-scaling headline: every GPU renders a full V-voice job (rank r holds voices
+    """N > 1 only, the companion of the strong headline: every GPU renders a full V-voice job (rank r holds voices
     r*V ... (r+1)*V - 1 of an N*V-voice render; the V-voice load is periodic in v by construction, so every rank installs
-    the same recipe on its own engine), partial mixes summed with the NCCL reduce overlapping the next render like the
-    headline loop.  Returns {"act": rendered voice-frames over all ranks, "ms": device ms (max over ranks), "launches":
-    rank 0's kernel launches + NCCL reduces, "e2e": the same job with a host buffer out of rank 0 every step (or None)}."""
+    the same recipe on a private engine that holds all its voices and joins a communicator of its own), partial mixes
+    summed by skb_reduce_mix overlapping the next render like the headline loop.  min(K, 50) steps.  Returns {"act":
+    rendered voice-frames over all ranks, "ms": device ms (max over ranks), "steps", "launches", "e2e": the same job with
+    a host buffer out of rank 0 every step (or None), "roof"}."""
     import torch
     import torch.distributed as dist
     from skred_b200 import Skred
     from skred_b200.host import load_engine_lib
+    from skred_b200.sharded import comm_init
     V, F, LF = a.voices, a.frames, a.launch_frames
+    K = min(a.steps, 50)
     eng = load_engine_lib()
     sk = Skred(V, device=local, rank=0, world=1, max_frames=max(F, 512), private=True)
-    total_frames = (a.warmup + a.steps) * F * 2 + 4 * F
+    total_frames = (a.warmup + K) * F * 2 + 4 * F
     wl = W.config5(V, seconds=600.0, luts=load_luts(), event_seconds=total_frames / SR + 1.0, stationary=True)
     W.install(sk, wl)
     ev = W.to_skb_events(wl["timed"])
     sk.lib.skb_shim_queue_events.argtypes = [C.c_void_p, C.c_int]
     sk.lib.skb_shim_queue_events(ev.ctypes.data, len(ev))
     sk.flush()
+    comm_init(sk, dist, eng)
     sk.lib.skb_shim_render_calls.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     comm = torch.cuda.Stream()
+    cp = C.c_void_p(comm.cuda_stream)
     mix = [torch.zeros((F, 2), dtype=torch.float32, device="cuda") for _ in range(2)]
-    rendered = [torch.cuda.Event() for _ in mix]
     reduced = [torch.cuda.Event() for _ in mix]
+    bad = [0]
 
     def step(i):
         k = i % 2
         stream.wait_event(reduced[k])
         if sk.lib.skb_shim_render_calls(LF, F // LF, mix[k].data_ptr(), sp) != 0:
-            raise RuntimeError("render failed")
-        rendered[k].record(stream)
-        with torch.cuda.stream(comm):
-            comm.wait_event(rendered[k])
-            dist.reduce(mix[k], dst=0, op=dist.ReduceOp.SUM)
-            reduced[k].record(comm)
+            bad[0] = 1
+        if eng.skb_reduce_mix(sk.engine, mix[k].data_ptr(), F, cp) != 0:
+            bad[0] = 1
+        reduced[k].record(comm)
         sk.lib.skb_shim_discard_gain()
 
     for i in range(a.warmup):
@@ -639,7 +722,7 @@ def weak_scaling_leg(a, local, world, stream, sp, peaks):
     before, launches_before = s_0.active_voice_frames, s_0.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for i in range(a.steps):
+    for i in range(K):
         step(a.warmup + i)
     stream.wait_stream(comm)
     e1.record(stream)
@@ -651,36 +734,35 @@ def weak_scaling_leg(a, local, world, stream, sp, peaks):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     n = torch.tensor([float(s_dev.active_voice_frames - before)], dtype=torch.float64, device="cuda")
     dist.all_reduce(n, op=dist.ReduceOp.SUM)
-    res = {"act": float(n.item()), "ms": float(t.item()),
-           "launches": int(s_dev.kernel_launches - launches_before) + a.steps, "e2e": None, "roof": None}
+    res = {"act": float(n.item()), "ms": float(t.item()), "steps": K,
+           "launches": int(s_dev.kernel_launches - launches_before) + K, "e2e": None, "roof": None}
     # dominant kernel alone on this GPU (the engine's CUDA events), as in the N = 1 line; rank 0's numbers are reported
     k_ms, k_act = [], []
     for i in range(3):
         a_b = sk.stats().active_voice_frames
-        step(a.warmup + a.steps + i)
+        step(a.warmup + K + i)
         stream.wait_stream(comm)
         eng.skb_sync(sk.engine, sp)
         st_k = sk.stats()
         k_ms.append(st_k.last_render_ms)
         k_act.append(st_k.active_voice_frames - a_b)
     if min(k_ms) > 0.0:
-        # every GPU runs the N = 1 launch (V voices, F frames), so the committed ncu counters of that launch apply
-        ncu = load_ncu_counters() if V == 65536 else None
-        if ncu and ncu.get("frames", 4096) != F:
+        ncu = load_ncu_counters()
+        if ncu and (ncu.get("frames") != F or ncu.get("voices_on_gpu") != V):
             ncu = None
         res["roof"] = roofline_objects(float(np.mean(k_act)), float(np.mean(k_ms)), V, F, peaks[0], peaks[1], peaks[2], ncu)
 
-    # end to end, host buffer on rank 0 every step (render -> NCCL reduce -> master volume -> D2H, in order), like the
+    # end to end, host buffer on rank 0 every step (render -> exchange step -> master volume -> D2H, in order), like the
     # N = 1 e2e through synth().  Every rank issues the same collectives whatever happens locally: a local failure
     # only sets a flag that is summed at the end (a raised exception on one rank would leave the others in a reduce).
     rank = dist.get_rank()
     out = np.zeros((F, 2), dtype=np.float32)
-    bad = [0]
 
     def step_e2e():
         if sk.lib.skb_shim_render_calls(LF, F // LF, mix[0].data_ptr(), sp) != 0:
             bad[0] = 1
-        dist.reduce(mix[0], dst=0, op=dist.ReduceOp.SUM)          # current stream = `stream` (set by the caller)
+        if eng.skb_reduce_mix(sk.engine, mix[0].data_ptr(), F, sp) != 0:
+            bad[0] = 1
         try:
             if rank == 0:
                 sk.finish(mix[0].data_ptr(), F, out, sp)
@@ -697,7 +779,7 @@ def weak_scaling_leg(a, local, world, stream, sp, peaks):
     eng.skb_sync(sk.engine, sp)
     s_b = sk.stats()
     t0 = time.perf_counter()
-    for _ in range(a.steps):
+    for _ in range(K):
         step_e2e()
     dist.barrier()
     torch.cuda.synchronize()
@@ -710,11 +792,13 @@ def weak_scaling_leg(a, local, world, stream, sp, peaks):
     dist.all_reduce(n, op=dist.ReduceOp.SUM)
     if float(v[1].item()) == 0.0 and float(v[0].item()) > 0.0:
         res["e2e"] = {"value": float(n.item()) / float(v[0].item()), "unit": UNIT,
-                      "h2d_bytes_per_step": (s_a.h2d_bytes - s_b.h2d_bytes) / a.steps,        # rank 0's engine
-                      "d2h_bytes_per_step": (s_a.d2h_bytes - s_b.d2h_bytes) / a.steps,
-                      "ms_per_step": float(v[0].item()) / a.steps * 1e3,
-                      "api": "per rank: %d x skb_shim_render_mix(%d) -> ncclReduce -> rank 0: skb_shim_finish into a host buffer"
+                      "h2d_bytes_per_step": (s_a.h2d_bytes - s_b.h2d_bytes) / K,        # rank 0's engine
+                      "d2h_bytes_per_step": (s_a.d2h_bytes - s_b.d2h_bytes) / K,
+                      "ms_per_step": float(v[0].item()) / K * 1e3,
+                      "api": "per rank: %d x skb_shim_render_mix(%d) -> skb_reduce_mix -> rank 0: skb_shim_finish into a host buffer"
                              % (F // LF, LF)}
+    dist.barrier()
+    eng.skb_comm_destroy(sk.engine)
     return res
 
 
@@ -759,7 +843,9 @@ def cpu_baseline(V):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--min-timed-s", type=float, default=0.5,
+                    help="repeat the EXACTLY-K-steps measurement until this much device time has been timed (0 = once)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--voices", type=int, default=65536)

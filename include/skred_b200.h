@@ -235,6 +235,40 @@ int  skb_snapshot(skb_engine *e, int first, int n, skb_voice_state *out);
 /* Host -> device overwrite of evolving state (checkpoint restore, tests). */
 int  skb_restore(skb_engine *e, int first, int n, const skb_voice_state *in);
 
+/* ---- the exchange step of the voice-sharded path (SURVEY 8e, 8b last row; north_star: "per-GPU stereo
+ *      partial mixes are summed with an NCCL reduce over NVLink") ------------------------------------
+ * The reference is one process with no device and no communication: these calls replace
+ * nothing, they are what lets a plain C host (skred.c:107-119 calls synth() from the audio callback)
+ * drive N B200s without Python.  NCCL (libnccl.so.2) is opened lazily by the first skb_comm_* call; an
+ * engine that never communicates does not need the library.
+ *
+ *   one process per GPU:   rank 0 calls skb_comm_unique_id and ships the SKB_COMM_ID_BYTES bytes to the
+ *                          other ranks over any transport; every rank then calls skb_comm_init_rank
+ *                          (ncclCommInitRank) on its engine (created with cfg.rank / cfg.world);
+ *   one process, N GPUs:   skb_comm_init_all(engines, n) — ncclCommInitAll over the engines' devices,
+ *                          engines[r] was created with cfg.rank = r, cfg.world = n.
+ *
+ * skb_reduce_mix launches what is pending (skb_flush) and sums d_mix[nframes][2] of all ranks into rank
+ * 0's d_mix on `stream` (NULL = engine stream), without host synchronisation; rank 0 then calls skb_finish.
+ * Cross-rank order of the sum:
+ *   SKB_COMM_NCCL_REDUCE  ncclReduce(sum, root 0): NCCL's tree / NVLS order — a deterministic function of
+ *                         (ranks, frames, NCCL version), run-to-run reproducible, not rank order;
+ *   SKB_COMM_ORDERED      partial mixes gathered on rank 0 (grouped ncclSend / ncclRecv) and added there
+ *                         in rank order 0, 1, ... n-1 by k_sum_ranks: the order SURVEY 5 asks for,
+ *                         independent of topology and NCCL version.
+ * Returns SKB_OK, SKB_ERR_STATE (no communicator / NCCL missing) or SKB_ERR_CUDA (NCCL error text in
+ * skb_error_string). */
+#define SKB_COMM_ID_BYTES 128
+#define SKB_COMM_NCCL_REDUCE 0
+#define SKB_COMM_ORDERED 1
+int  skb_comm_unique_id(void *id_out);
+int  skb_comm_init_rank(skb_engine *e, const void *id, int rank, int nranks);
+int  skb_comm_init_all(skb_engine *const *engines, int n);
+int  skb_comm_set_mode(skb_engine *e, int mode);
+int  skb_comm_size(const skb_engine *e);          /* ranks of the engine's communicator, 0 = none */
+int  skb_reduce_mix(skb_engine *e, float *d_mix, int nframes, void *stream);
+int  skb_comm_destroy(skb_engine *e);
+
 /* Does voice `v` belong to this engine's shard? (world > 1) */
 int  skb_owns_voice(skb_engine *e, int voice);
 

@@ -292,6 +292,21 @@ static void ensure_owner(skb_engine *e) {
   e->owner_valid = 1;
 }
 
+/* The exchange step (include/skred_b200.h, skb_comm_*): the CPU restatement has no devices and no NCCL.
+ * Hosts of the port sum the partial mixes themselves (tests: torch.distributed over gloo); the calls exist so
+ * that both implementations export the same ABI, and say so when used with more than one shard. */
+int skb_comm_unique_id(void *id_out) { (void)id_out; return SKB_ERR_STATE; }
+int skb_comm_init_rank(skb_engine *e, const void *id, int rank, int nranks) { (void)e; (void)id; (void)rank; (void)nranks; return SKB_ERR_STATE; }
+int skb_comm_init_all(skb_engine *const *engines, int n) { (void)engines; (void)n; return SKB_ERR_STATE; }
+int skb_comm_set_mode(skb_engine *e, int mode) { (void)e; (void)mode; return SKB_OK; }
+int skb_comm_size(const skb_engine *e) { (void)e; return 0; }
+int skb_comm_destroy(skb_engine *e) { (void)e; return SKB_OK; }
+int skb_reduce_mix(skb_engine *e, float *d_mix, int nframes, void *stream) {
+  (void)d_mix; (void)nframes; (void)stream;
+  if (!e) return SKB_ERR_ARG;
+  return e->cfg.world == 1 ? SKB_OK : SKB_ERR_STATE;
+}
+
 int skb_owns_voice(skb_engine *e, int voice) {
   if (!e || voice < 0 || voice >= e->n) return 0;
   ensure_owner(e);

@@ -34,7 +34,7 @@ NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v",
-              "-Xlinker", "-soname=libskred_b200.so"]
+              "-Xlinker", "-soname=libskred_b200.so", "-ldl"]
 HOST_CFLAGS = ["-O2", "-ffp-contract=off", "-fPIC", "-fno-strict-aliasing", "-g1"]
 DEFAULT_VOICES = [64, 1024, 4096, 65536]
 

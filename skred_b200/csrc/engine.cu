@@ -17,6 +17,8 @@
  * Reference mapping: synth() synth.c:502-630; see DESIGN.md.
  */
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -43,7 +45,7 @@ struct skb_engine {
   int err = SKB_OK;
   char errtxt[512] = {0};
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev_h2d = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t ev_h2d = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_comm = nullptr;
   bool timing_pending = false, wide_timing_pending = false;
 
   /* host mirror of what the host sent */
@@ -117,6 +119,11 @@ struct skb_engine {
 
   std::vector<skb_op> ops;
   skb_stats stats;
+
+  /* exchange step (skb_comm_*): NCCL communicator over the ranks of the voice-sharded render */
+  ncclComm_t comm = nullptr;
+  int comm_n = 0, comm_rank = 0, comm_mode = SKB_COMM_NCCL_REDUCE;
+  float2 *d_gather = nullptr; size_t gather_cap = 0;      /* rank 0, ordered mode: [rank][max_frames] partial mixes */
 
   /* pending batch of consecutive callbacks: rendered by ONE launch of k_render_free */
   struct {
@@ -221,6 +228,7 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
             cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_h2d, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreate(&e->ev_t0) == cudaSuccess && cudaEventCreate(&e->ev_t1) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_comm, cudaEventDisableTiming) == cudaSuccess &&
             cudaMalloc((void **)&e->d_pq, (size_t)SKB_NPQ * e->cap * sizeof(float4)) == cudaSuccess &&
             cudaMalloc((void **)&e->d_sq[0], (size_t)SKB_NSQ * e->cap * sizeof(float4)) == cudaSuccess &&
             cudaMalloc((void **)&e->d_sq[1], (size_t)SKB_NSQ * e->cap * sizeof(float4)) == cudaSuccess &&
@@ -273,6 +281,8 @@ void skb_destroy(skb_engine *e) {
   cudaSetDevice(e->cfg.device);
   batch_launch(e);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  skb_comm_destroy(e);
+  cudaFree(e->d_gather);
   cudaFree(e->d_pq); cudaFree(e->d_sq[0]); cudaFree(e->d_sq[1]); cudaFree(e->d_tables);
   cudaFree(e->d_bins); cudaFree(e->d_partials); cudaFree(e->d_mix); cudaFree(e->d_out);
   cudaFree(e->d_gain); cudaFree(e->d_noise); cudaFree(e->d_idx); cudaFree(e->d_recs);
@@ -295,6 +305,7 @@ void skb_destroy(skb_engine *e) {
   if (e->ev_h2d) cudaEventDestroy(e->ev_h2d);
   if (e->ev_t0) cudaEventDestroy(e->ev_t0);
   if (e->ev_t1) cudaEventDestroy(e->ev_t1);
+  if (e->ev_comm) cudaEventDestroy(e->ev_comm);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -835,6 +846,165 @@ static int sync_inputs(skb_engine *e, cudaStream_t st, bool defer_ops = false) {
     ops.clear();
   }
   return SKB_OK;
+}
+
+/* ---- exchange step: NCCL reduce of the partial mixes ------------------------------- */
+/* libnccl.so.2 is opened on first use: a single-GPU host never needs it.  In a process that already
+ * holds an NCCL (torch's bundled copy) the loader hands back that one. */
+struct NcclApi {
+  void *h = nullptr;
+  bool tried = false;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static bool nccl_load() {
+  if (g_nccl.tried) return g_nccl.h != nullptr;
+  g_nccl.tried = true;
+  const char *names[] = {getenv("SKB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  void *h = nullptr;
+  for (int i = 0; i < 3 && !h; i++) if (names[i] && names[i][0]) h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return false;
+#define SKB_NCCL_SYM(field, name) *(void **)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) { dlclose(h); return false; }
+  SKB_NCCL_SYM(GetUniqueId, "ncclGetUniqueId") SKB_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+  SKB_NCCL_SYM(CommInitAll, "ncclCommInitAll") SKB_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+  SKB_NCCL_SYM(Reduce, "ncclReduce") SKB_NCCL_SYM(Broadcast, "ncclBroadcast")
+  SKB_NCCL_SYM(Send, "ncclSend") SKB_NCCL_SYM(Recv, "ncclRecv")
+  SKB_NCCL_SYM(GroupStart, "ncclGroupStart") SKB_NCCL_SYM(GroupEnd, "ncclGroupEnd") SKB_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef SKB_NCCL_SYM
+  g_nccl.h = h;
+  return true;
+}
+
+#define NK(call)                                                                                   \
+  do {                                                                                             \
+    ncclResult_t _r = (call);                                                                      \
+    if (_r != ncclSuccess) return fail(e, SKB_ERR_CUDA, #call, g_nccl.GetErrorString(_r));          \
+  } while (0)
+
+int skb_comm_unique_id(void *id_out) {
+  if (!id_out) return SKB_ERR_ARG;
+  if (!nccl_load()) return SKB_ERR_STATE;
+  static_assert(SKB_COMM_ID_BYTES == NCCL_UNIQUE_ID_BYTES, "id size");
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return SKB_ERR_CUDA;
+  memcpy(id_out, &id, SKB_COMM_ID_BYTES);
+  return SKB_OK;
+}
+
+int skb_comm_init_rank(skb_engine *e, const void *id, int rank, int nranks) {
+  if (!e || !id || nranks < 1 || rank < 0 || rank >= nranks) return fail(e, SKB_ERR_ARG, "comm_init_rank: bad argument");
+  /* a sharded engine joins as its shard; an engine that holds ALL its voices (world = 1) may join any communicator
+   * (N independent full renders whose mixes are summed: the weak-scaling job of bench.py) */
+  if (e->cfg.world != 1 && (rank != e->cfg.rank || nranks != e->cfg.world))
+    return fail(e, SKB_ERR_ARG, "comm_init_rank: rank / nranks differ from the engine's voice shard (skb_config.rank / world)");
+  if (e->comm) return fail(e, SKB_ERR_STATE, "comm_init_rank: the engine already has a communicator");
+  if (!nccl_load()) return fail(e, SKB_ERR_STATE, "comm_init_rank: libnccl.so.2 not found (set SKB_NCCL_LIB)");
+  cudaSetDevice(e->cfg.device);
+  ncclUniqueId nid;
+  memcpy(&nid, id, SKB_COMM_ID_BYTES);
+  NK(g_nccl.CommInitRank(&e->comm, nranks, nid, rank));
+  e->comm_n = nranks; e->comm_rank = rank;
+  return e->err;
+}
+
+int skb_comm_init_all(skb_engine *const *engines, int n) {
+  if (!engines || n < 1) return SKB_ERR_ARG;
+  skb_engine *e = engines[0];
+  if (!nccl_load()) return fail(e, SKB_ERR_STATE, "comm_init_all: libnccl.so.2 not found (set SKB_NCCL_LIB)");
+  std::vector<int> devs((size_t)n);
+  for (int r = 0; r < n; r++) {
+    if (!engines[r] || engines[r]->cfg.rank != r || engines[r]->cfg.world != n || engines[r]->comm)
+      return fail(e, SKB_ERR_ARG, "comm_init_all: engines[r] must be created with rank = r, world = n and hold no communicator");
+    devs[r] = engines[r]->cfg.device;
+  }
+  std::vector<ncclComm_t> comms((size_t)n);
+  NK(g_nccl.CommInitAll(comms.data(), n, devs.data()));
+  for (int r = 0; r < n; r++) { engines[r]->comm = comms[r]; engines[r]->comm_n = n; engines[r]->comm_rank = r; }
+  return SKB_OK;
+}
+
+int skb_comm_set_mode(skb_engine *e, int mode) {
+  if (!e || (mode != SKB_COMM_NCCL_REDUCE && mode != SKB_COMM_ORDERED)) return fail(e, SKB_ERR_ARG, "comm_set_mode: bad mode");
+  e->comm_mode = mode;
+  return e->err;
+}
+
+int skb_comm_size(const skb_engine *e) { return (e && e->comm) ? e->comm_n : 0; }
+
+int skb_comm_destroy(skb_engine *e) {
+  if (!e) return SKB_ERR_ARG;
+  if (e->comm) {
+    cudaSetDevice(e->cfg.device);
+    if (e->last_stream) cudaStreamSynchronize(e->last_stream);
+    g_nccl.CommDestroy(e->comm);
+    e->comm = nullptr; e->comm_n = 0;
+  }
+  return SKB_OK;
+}
+
+/* rank 0, ordered mode: mix[f] = part[0][f] + part[1][f] + ... + part[n-1][f], left to right */
+__global__ void k_sum_ranks(const float2 *__restrict__ parts, int nranks, int stride, float2 *__restrict__ mix, int nframes) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nframes) return;
+  float2 a = parts[f];
+  for (int r = 1; r < nranks; r++) { const float2 b = parts[(size_t)r * stride + f]; a.x += b.x; a.y += b.y; }
+  mix[f] = a;
+}
+
+int skb_reduce_mix(skb_engine *e, float *d_mix, int nframes, void *stream) {
+  if (!e) return SKB_ERR_ARG;
+  if (!d_mix || nframes < 0 || nframes > e->cfg.max_frames) return fail(e, SKB_ERR_ARG, "reduce_mix: bad argument");
+  cudaSetDevice(e->cfg.device);
+  if (batch_launch(e)) return e->err;
+  if (!e->comm) {
+    if (e->cfg.world == 1) return e->err;                     /* one shard, nobody to add: the partial mix is the mix */
+    return fail(e, SKB_ERR_STATE, "reduce_mix: world > 1 and no communicator (skb_comm_init_rank / skb_comm_init_all)");
+  }
+  if (e->comm_n == 1 || nframes == 0) return e->err;
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  /* A caller may run the exchange on a stream of its own so that it overlaps the next render: the reduce is then
+   * ordered after everything queued on the render stream so far by an event (no host synchronisation, and the
+   * engine keeps launching on its render stream); making the NEXT writer of d_mix wait for `stream` is the caller's. */
+  if (e->last_stream && e->last_stream != st) {
+    CK(cudaEventRecord(e->ev_comm, e->last_stream));
+    CK(cudaStreamWaitEvent(st, e->ev_comm, 0));
+  } else if (!e->last_stream) {
+    e->last_stream = st;
+  }
+  if (e->comm_mode == SKB_COMM_NCCL_REDUCE) {
+    NK(g_nccl.Reduce(d_mix, d_mix, (size_t)nframes * 2, ncclFloat32, ncclSum, 0, e->comm, st));
+  } else {
+    const int mf = e->cfg.max_frames;
+    if (e->comm_rank == 0) {
+      if ((size_t)e->comm_n * mf > e->gather_cap) {
+        CK(cudaStreamSynchronize(st));
+        cudaError_t r = grow_dev(&e->d_gather, &e->gather_cap, (size_t)e->comm_n * mf);
+        if (r != cudaSuccess) return fail(e, SKB_ERR_CUDA, "gather alloc", cudaGetErrorString(r));
+      }
+      CK(cudaMemcpyAsync(e->d_gather, d_mix, (size_t)nframes * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+      NK(g_nccl.GroupStart());
+      for (int r = 1; r < e->comm_n; r++)
+        NK(g_nccl.Recv(e->d_gather + (size_t)r * mf, (size_t)nframes * 2, ncclFloat32, r, e->comm, st));
+      NK(g_nccl.GroupEnd());
+      k_sum_ranks<<<(nframes + 255) / 256, 256, 0, st>>>(e->d_gather, e->comm_n, mf, (float2 *)d_mix, nframes);
+      e->stats.kernel_launches++;
+    } else {
+      NK(g_nccl.Send(d_mix, (size_t)nframes * 2, ncclFloat32, 0, e->comm, st));
+    }
+  }
+  CK(cudaGetLastError());
+  return e->err;
 }
 
 int skb_owns_voice(skb_engine *e, int voice) {

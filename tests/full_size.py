@@ -71,9 +71,10 @@ def ref_worker(args):
     """One process: an independent reference instance renders `wl` (<= 64 voices) for sum(segs) frames as
     512-frame callbacks with the events of `wl["events"]` applied before their callback, and
     returns (mix or None, [state after each segment], seconds inside synth())."""
-    wl, segs, keep_mix, factory = args
+    wl, segs, keep_mix, factory = args[:4]
+    ref_v = args[4] if len(args) > 4 else REF_V
     from oracle import oracle as O
-    s = getattr(O, factory)(REF_V, run_seq=False)
+    s = getattr(O, factory)(ref_v, run_seq=False)
     n = wl["voices"]
     W.install(s, wl)
     ev = wl["events"]
@@ -110,11 +111,12 @@ def ref_worker(args):
     return mix, states, s.cpu_seconds
 
 
-def reference_by_subsets(wl, subsets, segs, keep_mix=True, procs=None, factory="RefSkred"):
-    """Render every voice subset on its own reference process.  Returns (float64 sum of the mixes or None,
-    [per checkpoint: {key: array over the concatenated subsets}], total CPU seconds)."""
+def reference_by_subsets(wl, subsets, segs, keep_mix=True, procs=None, factory="RefSkred", ref_v=REF_V):
+    """Render every voice subset on its own reference process (an instance compiled for VOICE_MAX = ref_v).
+    Returns (float64 sum of the mixes or None, [per checkpoint: {key: array over the concatenated subsets}],
+    total CPU seconds)."""
     import multiprocessing as mp
-    jobs = [(sub_wl, segs, keep_mix, factory) for sub_wl in select_many(wl, subsets)]
+    jobs = [(sub_wl, segs, keep_mix, factory, ref_v) for sub_wl in select_many(wl, subsets)]
     procs = max(1, min(procs or os.cpu_count() or 1, len(jobs)))
     total = None
     states = [dict() for _ in segs]

@@ -105,3 +105,30 @@ def test_config5_full_65536_voices_10min_subset_vs_reference(luts):
             reference_voices=256, cores=os.cpu_count())
     FS.assert_checkpoints_equal(ref_states, got_states)
     assert int(st.active_voice_frames) > 0.5 * V * wl["frames"]
+
+
+def test_config5_full_width_first_5s_vs_16_reference_shards(luts):
+    """configs[4], SURVEY 8d parity (i): ALL 65,536 voices, the first 5 s (220,500 frames = 430 callbacks and a
+    ragged 340-frame tail, ~33,000 timestamped events) against 16 instances of the compiled reference of 4,096
+    voices each (one per host core, voices of this load are independent), their mixes added in float64: the stereo
+    mix sample for sample <= 1e-5 of full scale, and every evolving word of every voice bit for bit at 2.5 s and 5 s."""
+    from skred_b200 import workloads as W
+    V, shard_v, frames = 65536, 4096, 5 * SR
+    if not O.have_ref(shard_v):
+        pytest.skip("compiled reference for VOICE_MAX = 4096 not present")
+    wl = W.config5(V, seconds=600.0, luts=luts, event_seconds=frames / float(SR) + 1.0, stationary=True)
+    wl["frames"] = frames
+    segs = FS.segments(frames, 2)
+    assert sum(segs) == frames and segs[0] % 8192 == 0
+    gpu = O.DropinCuda(V, run_seq=False)
+    got, got_states, t_gpu = FS.product_render(gpu, wl, segs)
+    t0 = time.perf_counter()
+    want, ref_states, cpu = FS.reference_by_subsets(wl, FS.chunks(range(V), shard_v), segs, ref_v=shard_v)
+    t_ref = time.perf_counter() - t0
+    err = float(np.max(np.abs(got.astype(np.float64) - want)))
+    _record("config5_full_width_5s", voices=V, frames=frames, events=len(wl["timed"]), product_synth_s=t_gpu,
+            reference_wall_s=t_ref, reference_cpu_s=cpu, cores=os.cpu_count(), max_abs_err=err,
+            peak=float(np.abs(want).max()))
+    assert err <= FULL_SCALE_TOL, err
+    assert float(np.abs(want).max()) > 1e-3
+    FS.assert_checkpoints_equal(ref_states, got_states)
