@@ -545,7 +545,8 @@ static int replan(skb_engine *e, cudaStream_t st) {
      * profiles/r01_s4_ab.txt), so the rows of a costly class (CZ and / or filter) go to a subset of the
      * CTAs sized by the class's share of the costly work — a CTA then renders ONE costly class — and the
      * light rows (plain, one-shot) fill every CTA up by LPT as before. */
-    auto deal = [](std::vector<std::pair<int, int>> items, int max_ctas, std::vector<int> &out, int *ctas_out, int *cap_out,
+    const bool tbl_affine = !(getenv("SKB_TBL_AFFINE") && atoi(getenv("SKB_TBL_AFFINE")) == 0);
+    auto deal = [tbl_affine](std::vector<std::pair<int, int>> items, int max_ctas, std::vector<int> &out, int *ctas_out, int *cap_out,
                    const std::vector<int> *rank) {
       const int n = (int)items.size();
       const int ctas = std::max(1, std::min(max_ctas, n));
@@ -586,7 +587,26 @@ static int replan(skb_engine *e, cudaStream_t st) {
           seen++;
           int k = (seen == nheavy) ? ctas - c0 : (int)((double)ctas * (double)csum[rk] / (double)hsum + 0.5);
           k = std::max(1, std::min(k, ctas - c0 - (nheavy - seen)));
-          std::vector<std::pair<int, int>> left = lpt(byc[rk], c0, c0 + k);
+          std::vector<std::pair<int, int>> left;
+          if (tbl_affine) {
+            /* TABLE-AFFINE: consecutive rows of a class hold voices sorted by wave table (feature_key), so a CTA that
+             * renders a CONTIGUOUS run of them sees 1-3 distinct tables and can stage all of them in shared memory
+             * (free_kernel.cuh, SKB_TMA_TABLES); LPT would deal neighbouring rows to different CTAs.  Rows of a class
+             * cost the same (one-shot rows a quarter), so cutting the row-ordered list at equal cost is as balanced. */
+            std::vector<std::pair<int, int>> byrow = byc[rk];
+            std::stable_sort(byrow.begin(), byrow.end(), [](const std::pair<int, int> &x, const std::pair<int, int> &y) {
+              return (x.second & ~SKB_ROW_WIDE) < (y.second & ~SKB_ROW_WIDE); });
+            long long acc = 0;
+            for (size_t i = 0; i < byrow.size(); i++) {
+              int c = c0 + (int)std::min<long long>((long long)k - 1, (acc * k) / std::max<long long>(csum[rk], 1));
+              while (c < c0 + k && (int)mine[c].size() >= rcap) c++;
+              if (c >= c0 + k) { left.push_back(byrow[i]); continue; }
+              mine[c].push_back(byrow[i]); load[c] += byrow[i].first;
+              acc += byrow[i].first;
+            }
+          } else {
+            left = lpt(byc[rk], c0, c0 + k);
+          }
           light.insert(light.end(), left.begin(), left.end());              /* (did not fit: anywhere) */
           c0 += k;
         }

@@ -106,6 +106,12 @@ def ref_worker(args):
         if done % BLOCK == 0 and ki < len(keys) and keys[ki] == k:
             s.apply(ev[k])
             ki += 1
+        elif done % BLOCK != 0:
+            # a ragged last callback of r frames ending at count c: seq(r) fires what is due by c + r (seq.c:171-178),
+            # i.e. the head of the NEXT callback's bucket; only valid at the very end of a job (nothing renders after it)
+            r = done % BLOCK
+            s.apply([c for t, c in sorted(wl.get("timed", []), key=lambda x: x[0])
+                     if W.callback_for_time(t) == k + 1 and t <= done + r])
         st = s.state()
         states.append({k_: st[k_][:n].copy() for k_ in STATE_KEYS})
     return mix, states, s.cpu_seconds

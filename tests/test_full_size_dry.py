@@ -32,11 +32,14 @@ def test_select_reindexes_an_arbitrary_subset(luts):
     assert sorted(sub["pcm_tau"]) == sorted(i for i, v in enumerate([5, 17, 50, 95]) if v in wl["pcm_tau"])
 
 
-@pytest.mark.parametrize("which", ["config4_dense", "config5_subset", "config2_release"])
+@pytest.mark.parametrize("which", ["config4_dense", "config4_dense_ragged_end", "config5_subset", "config2_release"])
 def test_full_size_harness_port_vs_reference_subsets(which, luts):
     _need()
-    if which == "config4_dense":
+    if which.startswith("config4_dense"):
         wl = W.config4(64, seconds=1.3, rate_hz=40.0)
+        if which.endswith("ragged_end"):
+            # a last callback of 340 frames with triggers due right after it: seq(340) fires what is due by c + 340
+            wl["frames"] = 6 * 8192 + 340
         V, subsets, n_ck = 64, FS.chunks(range(64), 16), 3
     elif which == "config2_release":
         wl = W.config2(64, seconds=0.9, luts=luts)
