@@ -159,6 +159,10 @@ typedef struct skb_config {
  * parallel, pass C runs the biquads).  Bit-identical state, same mix within the regrouping of the sum; measured
  * on B200 it does not pay (profiles/r01_time_split.txt), so the default is the sequential kernel. */
 #define SKB_CFG_WIDE 4u
+/* render every launch with k_render_rows (one CTA per 32-voice row, the warps are pipeline stages: row_kernel.cuh).  By
+ * default that kernel is used only when a launch holds few rows (one job cut over several GPUs); tests set the flag to
+ * run the whole parity suite through it.  Environment: SKB_ROWS=0 / 1 / 2 (never / always / auto), SKB_ROWS_MAX=<rows>. */
+#define SKB_CFG_ROWS 16u
 /* measuring aid: deal rows to CTAs by cost only (plain LPT) instead of class-affine (engine.cu: replan) */
 #define SKB_CFG_NO_AFFINE 8u
 
@@ -300,6 +304,7 @@ typedef struct skb_stats {
   double   host_us[4];        /* diagnostics, host microseconds accumulated: [0] launching a batch (sorting its ops, staging,
                                  H2D, kernel launches), [1] queueing skb_finish (wait for staging, gain H2D, k_finish, D2H),
                                  [2] waiting for the stream in skb_finish, [3] unused */
+  uint64_t rows_launches;     /* launches rendered by k_render_rows */
   uint64_t h2d_bytes, d2h_bytes; /* bytes the render path copied host -> device (parameter records, ops, per-launch staging
                                     block, noise and gain traces) and device -> host (stereo block, counters, tap) */
 } skb_stats;

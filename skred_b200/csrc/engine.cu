@@ -120,6 +120,9 @@ struct skb_engine {
   std::vector<skb_op> ops;
   skb_stats stats;
 
+  /* k_render_rows (row_kernel.cuh): 0 = never, 1 = every launch, 2 = launches of at most rows_auto_max free rows */
+  int rows_mode = 2, rows_auto_max = 0;
+
   /* exchange step (skb_comm_*): NCCL communicator over the ranks of the voice-sharded render */
   ncclComm_t comm = nullptr;
   int comm_n = 0, comm_rank = 0, comm_mode = SKB_COMM_NCCL_REDUCE;
@@ -211,6 +214,11 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
   if (e->cfg.max_frames < 512) e->cfg.max_frames = 512;
   e->n = cfg->n_voices;
   e->n_sm = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+  /* few voices on the GPU (one job cut over several GPUs): one CTA per row, the warps are pipeline stages */
+  e->rows_mode = (cfg->flags & SKB_CFG_ROWS) ? 1 : 2;
+  e->rows_auto_max = 2 * e->n_sm;
+  { const char *s = getenv("SKB_ROWS"); if (s && s[0]) e->rows_mode = atoi(s);
+    s = getenv("SKB_ROWS_MAX"); if (s && s[0]) e->rows_auto_max = atoi(s); }
   memset(&e->stats, 0, sizeof(e->stats));
   const int n = e->n, mf = e->cfg.max_frames;
   e->cap = ((n + 31) / 32) * 32 + 64 + 32 * 8;        /* + class padding of the free range */
@@ -256,6 +264,8 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
                                  (int)skb_free_smem_bytes()) == cudaSuccess &&
             cudaFuncSetAttribute(k_render_biquad, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)skb_free_smem_bytes()) == cudaSuccess &&
+            cudaFuncSetAttribute(k_render_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)skb_rows_smem_bytes()) == cudaSuccess &&
             cudaMallocHost((void **)&e->h_gain, (size_t)mf * sizeof(float)) == cudaSuccess &&
             cudaMallocHost((void **)&e->h_noise, (size_t)mf * sizeof(float)) == cudaSuccess &&
             cudaMallocHost((void **)&e->h_out, (size_t)mf * sizeof(float2)) == cudaSuccess &&
@@ -1052,10 +1062,14 @@ static int batch_launch(skb_engine *e) {
                     e->list_b[nwin].ctas > 0 && e->bins.empty() && (e->cfg.flags & SKB_CFG_WIDE) && !e->tap_on;
   /* per boundary: by (CTA that renders the voice, slot), queue order within a voice; the kernel gets one CSR
    * row per (boundary, CTA), so a CTA touches only its own ops — and most boundaries hold none for it */
+  /* few rows: one CTA per row (k_render_rows); its op buckets are the rows */
+  const bool rows = !wide && !e->tap_on && e->n_free_rows > 0 &&
+                    (e->rows_mode == 1 || (e->rows_mode == 2 && e->n_free_rows <= e->rows_auto_max));
   const std::vector<int> &cta_of = wide ? e->cta_of_row_wide : e->cta_of_row;
-  const int ncta = std::max(e->free_ctas, 1);
+  const int ncta = rows ? e->n_free_rows : std::max(e->free_ctas, 1);
   const int n_free_pad = e->n_free_pad;
-  auto cta_of_slot = [&cta_of, n_free_pad](int slot) { return (slot >= 0 && slot < n_free_pad) ? cta_of[(size_t)(slot >> 5)] : 0; };
+  auto cta_of_slot = [&cta_of, n_free_pad, rows](int slot) {
+    return (slot >= 0 && slot < n_free_pad) ? (rows ? (slot >> 5) : cta_of[(size_t)(slot >> 5)]) : 0; };
   for (size_t i = 0; i < nops; i++) e->batch.ops[i]._pad = cta_of_slot(e->batch.ops[i].voice);   /* bucket key; the kernel ignores it */
   cudaError_t r;
   if (wait_staging(e)) return e->err;
@@ -1125,7 +1139,8 @@ static int batch_launch(skb_engine *e) {
   const skb_engine::RowList lb = wide ? e->list_b[nwin] : skb_engine::RowList();
   const int groups_b = wide ? lb.ctas * (lb.rows_cap / SKB_CTA_WARPS) : 0;
   const int groups_c = (wide && e->list_c.ctas > 0) ? e->list_c.ctas * (e->list_c.rows_cap / SKB_CTA_WARPS) : 0;
-  const int n_prows_now = wide ? e->free_groups + groups_b + groups_c : e->n_prows;
+  /* rows mode: the bins keep their partial rows [free_groups, n_prows), the free rows follow at n_prows */
+  const int n_prows_now = wide ? e->free_groups + groups_b + groups_c : (rows ? e->n_prows + e->n_free_rows : e->n_prows);
   const size_t n_prow = (size_t)std::max(n_prows_now, 1);
   if (n_prow * (size_t)e->cfg.max_frames > e->partials_cap) {
     CK(cudaStreamSynchronize(st));
@@ -1151,7 +1166,7 @@ static int batch_launch(skb_engine *e) {
     fa.cta_rowlist = wide ? e->d_lists + e->list_a_wide.off : e->d_ctarows; fa.rows_cap = e->rows_cap;
     fa.tables = e->d_tables; fa.noise = e->d_noise;
     fa.nframes = nframes; fa.ssc_before = (unsigned long long)e->batch.ssc0;
-    fa.win_frames = d_winp; fa.win_ob = d_winp + nwin; fa.nwin = nwin;
+    fa.win_frames = d_winp; fa.win_ob = d_winp + nwin; fa.nwin = nwin; fa.ob_stride = ncta + 1;
     fa.bops = d_bopsp; fa.wake = d_wake;
     fa.ctarows = e->d_partials; fa.row_stride = nframes;
     fa.envbuf = e->d_envbuf; fa.counters = e->d_counters; fa.cta_phase = e->d_ctaphase;
@@ -1165,7 +1180,11 @@ static int batch_launch(skb_engine *e) {
     fa.warp_diag = e->d_ctaphase ? e->d_ctaphase + (size_t)e->n_sm * 8 : nullptr;
     if (wide)       /* "no snapshot" = finished: group 0 of every window's snapshot */
       CK(cudaMemsetAsync(e->d_snap, 0x01, (size_t)nwin * e->cap * sizeof(float4), st));
-    if (e->tap_on) k_render_free_tap<<<e->free_ctas, SKB_CTA_THREADS, skb_free_smem_bytes(), st>>>(fa);
+    if (rows) {
+      fa.group0 = e->n_prows;
+      k_render_rows<<<e->n_free_rows, RP_THREADS, skb_rows_smem_bytes(), st>>>(fa);
+      e->stats.rows_launches++;
+    } else if (e->tap_on) k_render_free_tap<<<e->free_ctas, SKB_CTA_THREADS, skb_free_smem_bytes(), st>>>(fa);
     else k_render_free<<<e->free_ctas, SKB_CTA_THREADS, skb_free_smem_bytes(), st>>>(fa);
     e->stats.kernel_launches++;
     if (wide) {
@@ -1200,7 +1219,8 @@ static int batch_launch(skb_engine *e) {
   if (n_prows_now > 0) {
     dim3 blk(SKB_RED_X, SKB_RED_Y);
     dim3 grd((nframes + SKB_RED_X - 1) / SKB_RED_X, std::max(1, std::min(SKB_RED_CHUNKS, n_prows_now / 16)));
-    k_reduce_rows<<<grd, blk, 0, st>>>(e->d_partials, n_prows_now, nframes, nframes, e->d_part2,
+    const int skip = rows ? e->free_groups : 0;                /* rows mode: k_render_free's rows are not written */
+    k_reduce_rows<<<grd, blk, 0, st>>>(e->d_partials + (size_t)skip * nframes, n_prows_now - skip, nframes, nframes, e->d_part2,
                                        e->d_tickets, (float2 *)e->batch.mix);
     e->stats.kernel_launches++;
   } else {

@@ -324,8 +324,9 @@ __device__ __forceinline__ void dev_apply_op(VoiceS &s, const skb_op &op) {
 }
 
 
-/* K1  render_free: free_kernel.cuh */
+/* K1  render_free: free_kernel.cuh; K1b render_rows (few voices per GPU): row_kernel.cuh */
 #include "free_kernel.cuh"
+#include "row_kernel.cuh"
 
 /* ======================================================================== */
 /* K2  render_bins: modulation groups, frame-lock-step                       */
@@ -416,6 +417,109 @@ k_render_bins(const float4 *__restrict__ pq, float4 *__restrict__ sq, int cap,
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) na += __shfl_xor_sync(0xffffffffu, na, d);
   if (lane == 0 && na) atomicAdd(counter, (unsigned long long)na);
+}
+
+/* K2w  render_bins_warp: modulation groups of <= 32 voices, ONE WARP per bin.
+ * The same frame-lock-step rule as k_render_bins (synth.c:526 loop order: modulator m < n is read at the current
+ * frame, m > n at the previous one), but the voices of a bin are the lanes of one warp: the same-frame dependency
+ * levels are separated by __syncwarp() instead of CTA barriers, the bin's voice_sample[] exchange is 64 floats of
+ * shared memory private to the warp, and the stereo sum goes through the warp's tile 16 frames at a time (the
+ * transposed reduce of k_render_free) instead of ten shuffles and a thread-0 loop per frame.  Because nothing of a
+ * bin is shared with another warp, bins ride inside BATCHED launches like free voices: the launch renders `nwin`
+ * consecutive callbacks and the lane that owns a voice replays the ops queued for the boundary before each of them
+ * (seq.c:170-178) on its registers.  Ops of bin voices sit in bucket `ob_bucket` of the per-window CSR. */
+#define SKB_BINW_WARPS 4
+struct BinWarpArgs {
+  const float4 *pq; float4 *sq; int cap;
+  const skb_bin_desc *bins; int nbins;
+  const float *tables; const float *noise;
+  int nframes; unsigned long long ssc_before;
+  const int *win_frames; const int *win_ob; int nwin, ob_stride, ob_bucket;
+  const skb_op *bops;
+  float2 *partials; int row_stride;
+  unsigned long long *counter;
+  float2 *tap; const int *voice_of_slot; int tap_n;
+};
+
+__global__ void __launch_bounds__(SKB_BINW_WARPS * 32) k_render_bins_warp(const __grid_constant__ BinWarpArgs a) {
+  __shared__ float s_vs[SKB_BINW_WARPS][2][32];
+  __shared__ float s_inc[SKB_BINW_WARPS][32];
+  __shared__ float2 s_tile[SKB_BINW_WARPS][SKB_TILE_FLOAT2];
+  __shared__ float2 s_row[SKB_BINW_WARPS][SKB_UNIT];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * SKB_BINW_WARPS + warp;
+  if (b >= a.nbins) return;                                   /* (warps are independent: no CTA barrier below) */
+  const skb_bin_desc bd = a.bins[b];
+  const bool live = lane < bd.size;
+  const int slot = bd.slot0 + (live ? lane : 0);
+  VoiceP p; VoiceS s; VoiceK k;
+  load_params(a.pq, a.cap, slot, p);
+  load_state(a.sq, a.cap, slot, s);
+  if (!live) { p.amp = 0.0f; p.flags = SKB_F_SMOOTHER; p.cz_mode = 0; p.fmode = 0; p.level = 0;
+               p.fm_ref = SKB_REF_NONE; p.am_ref = SKB_REF_NONE; p.pm_ref = SKB_REF_NONE; p.cz_ref = SKB_REF_NONE; p.sh_max = 0; p.quant = 0; }
+  derive_consts(p, k);
+  float *vs0 = s_vs[warp][0], *vs1 = s_vs[warp][1];
+  float2 *mytile = s_tile[warp], *myrow = s_row[warp];
+  vs0[lane] = live ? s.sample : 0.0f;
+  vs1[lane] = 0.0f;
+  s_inc[warp][lane] = live ? p.inc : 0.0f;
+  const bool wants_noise = live && (p.flags & SKB_F_NOISE);
+  float2 *out_row = a.partials + (size_t)bd.row * a.row_stride;
+  float2 *tap_lane = nullptr;                                 /* per-voice tap, synth.c:533-611 */
+  if (a.tap_n && live) { const int tv = __ldg(a.voice_of_slot + slot); if (tv >= 0) tap_lane = a.tap + tv; }
+  __syncwarp();
+  int fr = 0;                                                 /* launch-relative frame */
+  for (int w = 0; w < a.nwin; w++) {
+    /* ops of the boundary before window w, replayed by the lane that owns the voice */
+    const int ob = a.win_ob ? __ldg(a.win_ob + (size_t)w * a.ob_stride + a.ob_bucket) : 0;
+    const int oe = a.win_ob ? __ldg(a.win_ob + (size_t)w * a.ob_stride + a.ob_bucket + 1) : 0;
+    if (oe > ob) {
+      if (live) {
+        int lo = ob, hi = oe;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(&a.bops[mid].voice) < slot) lo = mid + 1; else hi = mid; }
+        for (int i = lo; i < oe; i++) {
+          const skb_op op = a.bops[i];
+          if (op.voice != slot) break;
+          dev_apply_op(s, op);
+        }
+        ((fr & 1) ? vs1 : vs0)[lane] = s.sample;              /* what modulators read as "previous frame" (voice_reset clears it) */
+      }
+      __syncwarp();
+    }
+    const int wn = __ldg(a.win_frames + w);
+    for (int f0 = 0; f0 < wn; f0 += SKB_UNIT) {
+      const int cnt = min(SKB_UNIT, wn - f0);
+      for (int j = 0; j < cnt; j++, fr++) {
+        BinMods mod;
+        mod.prev = (fr & 1) ? vs1 : vs0;
+        float *cur = (fr & 1) ? vs0 : vs1;
+        mod.cur = cur;
+        mod.inc = s_inc[warp];
+        const float white = wants_noise ? __ldg(a.noise + fr) : 0.0f;
+        float2 o = make_float2(0.0f, 0.0f);
+        for (int lvl = 0; lvl < bd.nlevels; lvl++) {
+          if (live && p.level == lvl) {
+            o = voice_frame<true>(p, k, s, a.ssc_before + (unsigned long long)(fr + 1), white, a.tables, mod);
+            cur[lane] = s.sample;
+          }
+          __syncwarp();
+        }
+        if (tap_lane) tap_lane[(size_t)fr * a.tap_n] = o;
+        mytile[j * SKB_TILE_STRIDE + lane] = o;
+      }
+      for (int j = cnt; j < SKB_UNIT; j++) mytile[j * SKB_TILE_STRIDE + lane] = make_float2(0.0f, 0.0f);
+      __syncwarp();
+      reduce_unit(mytile, myrow, lane, cnt);
+      __syncwarp();
+      if (lane < cnt) out_row[fr - cnt + lane] = myrow[lane];
+      __syncwarp();
+    }
+  }
+  if (live) store_state(a.sq, a.cap, slot, s);
+  int na = live ? s.nact : 0;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) na += __shfl_xor_sync(0xffffffffu, na, d);
+  if (lane == 0 && na) atomicAdd(a.counter, (unsigned long long)na);
 }
 
 /* ======================================================================== */

@@ -16,8 +16,9 @@ V = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 EV = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 BLK = int(sys.argv[4]) if len(sys.argv) > 4 else 512          # frames per synth() call
+WORLD = int(sys.argv[5]) if len(sys.argv) > 5 else 1           # render only rank 0's shard of a job cut WORLD ways
 luts = dict(np.load(os.path.join(ROOT, "tests", "golden", "notamy_luts.npz")))
-sk = Skred(V, max_frames=max(512, BLK))
+sk = Skred(V, max_frames=max(512, BLK), rank=0, world=WORLD)
 wl = W.config5(V, seconds=600.0, luts=luts, event_seconds=(N * BLK / 44100.0 + 1.0) if EV else 0.0, stationary=True)
 W.install(sk, wl)
 if EV:
@@ -31,7 +32,7 @@ for k in range(N):
     sk.lib.synth(out.ctypes.data, None, BLK, 2, None)
     st = sk.stats()
     cr = [int(a - b) for a, b in zip(st.class_rows, prev.class_rows)]
-    act = (st.active_voice_frames - prev.active_voice_frames) / (V * BLK)
+    act = (st.active_voice_frames - prev.active_voice_frames) / (V // WORLD * BLK)
     if k < 3 or k % 8 == 0 or k == N - 1:
         print("launch %3d  kernel %.3f ms (A %.3f B %.3f C+reduce %.3f)  active %.3f  rows/class [none none+f pw pw+f pow pow+f mixed generic] = %s" %
               (k, st.last_render_ms, st.last_wide_ms[0], st.last_wide_ms[1], st.last_wide_ms[2], act, cr), flush=True)

@@ -1,0 +1,13 @@
+#!/bin/bash
+# round 2, call 5: k_render_rows — the whole parity suite through it (SKB_ROWS=1), then its speed on one GPU's shard
+mkdir -p gpurun_out
+( time SKB_ROWS=1 timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py tests/test_event_fuzz.py -m gpu -q -x ) > gpurun_out/pytest_rows.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_rows.log
+grep -v "^#" gpurun_out/pytest_rows.log | tail -30 | cut -c1-300
+rm -f gpurun_out/rows_speed.txt
+for w in 8 4 2; do
+  for m in 0 1; do
+    echo "== world $w SKB_ROWS=$m" >> gpurun_out/rows_speed.txt
+    SKB_EARLY_FLUSH=0 SKB_ROWS=$m timeout 300 python tools/bench_probe.py 65536 12 1 8192 $w 2>&1 | grep -E "^launch +(8|11)" >> gpurun_out/rows_speed.txt
+  done
+done
+cat gpurun_out/rows_speed.txt
