@@ -159,9 +159,10 @@ typedef struct skb_config {
  * parallel, pass C runs the biquads).  Bit-identical state, same mix within the regrouping of the sum; measured
  * on B200 it does not pay (profiles/r01_time_split.txt), so the default is the sequential kernel. */
 #define SKB_CFG_WIDE 4u
-/* render every launch with k_render_rows (one CTA per 32-voice row, the warps are pipeline stages: row_kernel.cuh).  By
- * default that kernel is used only when a launch holds few rows (one job cut over several GPUs); tests set the flag to
- * run the whole parity suite through it.  Environment: SKB_ROWS=0 / 1 / 2 (never / always / auto), SKB_ROWS_MAX=<rows>. */
+/* render every launch with k_render_rows (one CTA per 32-voice row, the warps are pipeline stages: row_kernel.cuh), the
+ * kernel built for launches that leave the SMs nearly empty (one job cut over several GPUs).  Bit-identical state (the
+ * whole parity suite runs through it with SKB_ROWS=1); measured no faster than k_render_free, so it is opt-in.
+ * Environment: SKB_ROWS=0 / 1 / 2 (never / always / launches of at most SKB_ROWS_MAX rows). */
 #define SKB_CFG_ROWS 16u
 /* measuring aid: deal rows to CTAs by cost only (plain LPT) instead of class-affine (engine.cu: replan) */
 #define SKB_CFG_NO_AFFINE 8u
@@ -305,6 +306,7 @@ typedef struct skb_stats {
                                  H2D, kernel launches), [1] queueing skb_finish (wait for staging, gain H2D, k_finish, D2H),
                                  [2] waiting for the stream in skb_finish, [3] unused */
   uint64_t rows_launches;     /* launches rendered by k_render_rows */
+  uint64_t migrated_voices;   /* voices whose state moved to another GPU at a re-plan (a modulation edge joined two shards) */
   uint64_t h2d_bytes, d2h_bytes; /* bytes the render path copied host -> device (parameter records, ops, per-launch staging
                                     block, noise and gain traces) and device -> host (stereo block, counters, tap) */
 } skb_stats;

@@ -77,6 +77,11 @@ typedef struct skb_event {
   int32_t  code;
   float    a0, a1;
 } skb_event;            /* 24 bytes */
+/* Order.  Due events fire in TIME order, first come first served among equal times.  The reference's seq() scans its
+ * 1,024 work_queue slots in SLOT order (seq.c:171-178; a slot is whatever queue_item found free, seq.c:243-257), so two
+ * of its items that become due at the same callback with different times fire in an order that depends on which slots
+ * happened to be free.  This queue does not reproduce that accident; hosts that need it keep using seq.c's own
+ * work_queue on top of the drop-in (wire.c / seq.c run unmodified over the shim: tests/test_gpu_parity.py). */
 int  skb_shim_queue_events(const skb_event *ev, int n);
 int  skb_shim_pending_events(void);
 

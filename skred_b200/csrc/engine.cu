@@ -34,7 +34,7 @@
 #include "voice_kernels.cuh"
 
 #define SKB_N_COUNTERS 20      /* rendered voice-frames (free, bins), live rows per class, phase clocks, CTA batches */
-#define SKB_BIN_PACK 128      /* small components are packed into bins of <= this many voices */
+#define SKB_BIN_WARP 32       /* components of <= 32 voices are packed into bins of <= 32: one warp per bin */
 #define SKB_BIN_MAX 1024      /* one CTA per bin: hard upper bound of a component */
 
 struct TableDesc { size_t off; int size; };
@@ -64,6 +64,7 @@ struct skb_engine {
   std::vector<skb_bin_desc> bins;
   std::vector<uint64_t> edge_sig;                   /* per voice: hash of its live edges (re-plan trigger) */
   int n_free = 0, n_free_pad = 0, n_slots = 0, n_free_rows = 0, max_bin_threads = 0;
+  int n_small_bins = 0;              /* bins [0, n_small_bins) hold <= 32 voices each (k_render_bins_warp), the rest one big component each */
   int rows_cap = 0;                  /* entries per CTA in d_ctarows */
   int *d_ctarows = nullptr; size_t ctarows_cap = 0;
   std::vector<int> h_ctarows;
@@ -127,6 +128,8 @@ struct skb_engine {
   ncclComm_t comm = nullptr;
   int comm_n = 0, comm_rank = 0, comm_mode = SKB_COMM_NCCL_REDUCE;
   float2 *d_gather = nullptr; size_t gather_cap = 0;      /* rank 0, ordered mode: [rank][max_frames] partial mixes */
+  skb_voice_state *d_mig = nullptr; size_t mig_cap = 0;   /* records of voices that change GPUs at a re-plan */
+  int *d_migidx = nullptr; size_t migidx_cap = 0;
 
   /* pending batch of consecutive callbacks: rendered by ONE launch of k_render_free */
   struct {
@@ -156,6 +159,8 @@ const char *skb_backend_name(void) { return "cuda-sm100a"; }
 static double host_now_us() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return 1e6 * (double)t.tv_sec + 1e-3 * (double)t.tv_nsec; }
 
 static int batch_launch(skb_engine *e);
+/* can the pending ops ride inside a batched launch?  Free voices always; modulation bins when every bin is a warp bin */
+static inline bool bins_batch_ok(const skb_engine *e) { return e->bins.empty() || (int)e->bins.size() == e->n_small_bins; }
 
 static int fail(skb_engine *e, int code, const char *what, const char *detail = nullptr) {
   if (e && e->err == SKB_OK) {
@@ -170,6 +175,51 @@ static int fail(skb_engine *e, int code, const char *what, const char *detail = 
     cudaError_t _r = (call);                                                       \
     if (_r != cudaSuccess) return fail(e, SKB_ERR_CUDA, #call, cudaGetErrorString(_r)); \
   } while (0)
+
+/* ---- exchange step: NCCL reduce of the partial mixes (SURVEY 8e) ------------------------------- */
+/* libnccl.so.2 is opened on first use: a single-GPU host never needs it.  In a process that already
+ * holds an NCCL (torch's bundled copy) the loader hands back that one. */
+struct NcclApi {
+  void *h = nullptr;
+  bool tried = false;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static bool nccl_load() {
+  if (g_nccl.tried) return g_nccl.h != nullptr;
+  g_nccl.tried = true;
+  const char *names[] = {getenv("SKB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  void *h = nullptr;
+  for (int i = 0; i < 3 && !h; i++) if (names[i] && names[i][0]) h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return false;
+#define SKB_NCCL_SYM(field, name) *(void **)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) { dlclose(h); return false; }
+  SKB_NCCL_SYM(GetUniqueId, "ncclGetUniqueId") SKB_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+  SKB_NCCL_SYM(CommInitAll, "ncclCommInitAll") SKB_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+  SKB_NCCL_SYM(Reduce, "ncclReduce") SKB_NCCL_SYM(Broadcast, "ncclBroadcast")
+  SKB_NCCL_SYM(Send, "ncclSend") SKB_NCCL_SYM(Recv, "ncclRecv")
+  SKB_NCCL_SYM(GroupStart, "ncclGroupStart") SKB_NCCL_SYM(GroupEnd, "ncclGroupEnd") SKB_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef SKB_NCCL_SYM
+  g_nccl.h = h;
+  return true;
+}
+
+#define NK(call)                                                                                   \
+  do {                                                                                             \
+    ncclResult_t _r = (call);                                                                      \
+    if (_r != ncclSuccess) return fail(e, SKB_ERR_CUDA, #call, g_nccl.GetErrorString(_r));          \
+  } while (0)
+
 
 template <class T>
 static cudaError_t grow_dev(T **p, size_t *cap, size_t need) {
@@ -215,7 +265,9 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
   e->n = cfg->n_voices;
   e->n_sm = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
   /* few voices on the GPU (one job cut over several GPUs): one CTA per row, the warps are pipeline stages */
-  e->rows_mode = (cfg->flags & SKB_CFG_ROWS) ? 1 : 2;
+  /* measured on B200 (profiles/r02_rows_kernel.txt): 0.40-0.44 ms against 0.445 ms of k_render_free for an 8,192-frame
+   * launch of 8,192 voices, slower from 16,384 voices up — not enough to switch by default: opt-in */
+  e->rows_mode = (cfg->flags & SKB_CFG_ROWS) ? 1 : 0;
   e->rows_auto_max = 2 * e->n_sm;
   { const char *s = getenv("SKB_ROWS"); if (s && s[0]) e->rows_mode = atoi(s);
     s = getenv("SKB_ROWS_MAX"); if (s && s[0]) e->rows_auto_max = atoi(s); }
@@ -292,7 +344,7 @@ void skb_destroy(skb_engine *e) {
   batch_launch(e);
   if (e->stream) cudaStreamSynchronize(e->stream);
   skb_comm_destroy(e);
-  cudaFree(e->d_gather);
+  cudaFree(e->d_gather); cudaFree(e->d_mig); cudaFree(e->d_migidx);
   cudaFree(e->d_pq); cudaFree(e->d_sq[0]); cudaFree(e->d_sq[1]); cudaFree(e->d_tables);
   cudaFree(e->d_bins); cudaFree(e->d_partials); cudaFree(e->d_mix); cudaFree(e->d_out);
   cudaFree(e->d_gain); cudaFree(e->d_noise); cudaFree(e->d_idx); cudaFree(e->d_recs);
@@ -456,11 +508,39 @@ static int replan(skb_engine *e, cudaStream_t st) {
   std::vector<int32_t> old_owner;
   if (e->planned && world > 1) old_owner = e->owner;
   skb_components(e->par.data(), n, e->comp.data());
-  skb_partition(e->comp.data(), n, world, e->owner.data());
+  /* ownership is sticky: a re-plan keeps every voice on its rank unless its component merged with one that lives elsewhere */
+  skb_partition_stable(e->comp.data(), n, world, old_owner.empty() ? nullptr : old_owner.data(), e->owner.data());
+  std::vector<int32_t> migrating;                     /* voices whose evolving state has to change GPUs, ascending */
   if (e->planned && world > 1 && e->stats.frames_rendered > 0) {
     for (int v = 0; v < n; v++)
-      if (old_owner[v] != e->owner[v])
-        return fail(e, SKB_ERR_STATE, "re-plan moved a voice to another shard: migrate its state with skb_snapshot/skb_restore");
+      if (old_owner[v] != e->owner[v]) migrating.push_back(v);
+    if (!migrating.empty() && !e->comm) {
+      e->owner = old_owner;
+      return fail(e, SKB_ERR_STATE, "a modulation edge joined voices of two shards: their state has to move, which needs the engines' communicator (skb_comm_init_rank / skb_comm_init_all)");
+    }
+  }
+  if (!migrating.empty()) {
+    /* every rank computes the same list (the host mirrors are identical).  The old owner of each voice gathers its record
+     * from its (old) slot; one broadcast per source rank carries the records to everybody; the new owners scatter the
+     * ones they now own once the new slots exist (below).  Order on `st`: after every launch that wrote the state. */
+    const size_t nm = migrating.size();
+    cudaError_t rr;
+    if ((rr = grow_dev(&e->d_mig, &e->mig_cap, nm)) != cudaSuccess || (rr = grow_dev(&e->d_migidx, &e->migidx_cap, nm)) != cudaSuccess)
+      return fail(e, SKB_ERR_CUDA, "migration alloc", cudaGetErrorString(rr));
+    std::stable_sort(migrating.begin(), migrating.end(), [&old_owner](int32_t a, int32_t b) { return old_owner[a] < old_owner[b]; });
+    std::vector<int> idx(nm);
+    for (size_t i = 0; i < nm; i++) idx[i] = (old_owner[migrating[i]] == rank) ? e->slot_of_voice[migrating[i]] : -1;
+    CK(cudaMemcpyAsync(e->d_migidx, idx.data(), nm * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));                    /* pageable source */
+    k_gather_state<<<(int)((nm + 127) / 128), 128, 0, st>>>(e->d_sq[e->cur], e->cap, e->d_migidx, (int)nm, e->d_mig);
+    e->stats.kernel_launches++;
+    for (size_t i = 0; i < nm;) {
+      size_t j = i;
+      const int src = old_owner[migrating[i]];
+      while (j < nm && old_owner[migrating[j]] == src) j++;
+      NK(g_nccl.Broadcast(e->d_mig + i, e->d_mig + i, (j - i) * sizeof(skb_voice_state), ncclChar, src, e->comm, st));
+      i = j;
+    }
   }
   std::vector<int32_t> csize(n, 0);
   for (int v = 0; v < n; v++) csize[e->comp[v]]++;
@@ -499,14 +579,19 @@ static int replan(skb_engine *e, cudaStream_t st) {
       if (e->owner[v] == rank && csize[e->comp[v]] > 1) members[ridx[e->comp[v]]].push_back(v);
   }
   e->bins.clear();
-  std::vector<std::vector<int32_t>> binv;
+  /* components of <= 32 voices are packed into bins of <= 32 and rendered one WARP per bin (k_render_bins_warp, batched
+   * launches with in-kernel boundary ops); a larger component gets a CTA of its own (k_render_bins) */
+  std::vector<std::vector<int32_t>> binv, binv_big;
   for (size_t i = 0; i < roots.size(); i++) {
     const int sz = (int)members[i].size();
     if (sz > SKB_BIN_MAX)
       return fail(e, SKB_ERR_CAPACITY, "a modulation group has more than 1024 voices");
-    if (binv.empty() || (int)binv.back().size() + sz > SKB_BIN_PACK) binv.push_back(std::vector<int32_t>());
+    if (sz > SKB_BIN_WARP) { binv_big.push_back(members[i]); continue; }
+    if (binv.empty() || (int)binv.back().size() + sz > SKB_BIN_WARP) binv.push_back(std::vector<int32_t>());
     binv.back().insert(binv.back().end(), members[i].begin(), members[i].end());
   }
+  e->n_small_bins = (int)binv.size();
+  binv.insert(binv.end(), binv_big.begin(), binv_big.end());
   int slot = e->n_free_pad;
   e->n_free_rows = e->n_free_pad / 32;
   /* partial-row groups: one per (CTA, batch) of k_render_free, then the bins 16 to a group */
@@ -718,7 +803,7 @@ static int replan(skb_engine *e, cudaStream_t st) {
       d.nlevels = std::max(d.nlevels, lv + 1);
     }
     e->bins.push_back(d);
-    e->max_bin_threads = std::max(e->max_bin_threads, (d.size + 31) & ~31);
+    if ((int)b >= e->n_small_bins) e->max_bin_threads = std::max(e->max_bin_threads, (d.size + 31) & ~31);
     slot += d.size;
   }
   e->n_slots = slot;
@@ -741,6 +826,16 @@ static int replan(skb_engine *e, cudaStream_t st) {
     k_permute_state<<<(total + 255) / 256, 256, 0, st>>>(e->d_sq[e->cur], e->d_sq[e->cur ^ 1], e->cap, e->d_idx, e->cap);
     e->stats.kernel_launches++;
     e->cur ^= 1;
+  }
+  if (!migrating.empty()) {
+    const size_t nm = migrating.size();
+    std::vector<int> idx(nm);
+    for (size_t i = 0; i < nm; i++) idx[i] = (e->owner[migrating[i]] == rank) ? e->slot_of_voice[migrating[i]] : -1;
+    CK(cudaMemcpyAsync(e->d_migidx, idx.data(), nm * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    k_scatter_state<<<(int)((nm + 127) / 128), 128, 0, st>>>(e->d_sq[e->cur], e->cap, e->d_migidx, (int)nm, e->d_mig);
+    e->stats.kernel_launches++;
+    e->stats.migrated_voices += nm;
   }
   CK(cudaMemsetAsync(e->d_pq, 0, (size_t)SKB_NPQ * e->cap * sizeof(float4), st));
   CK(cudaEventRecord(e->ev_h2d, st));
@@ -837,7 +932,7 @@ static int sync_inputs(skb_engine *e, cudaStream_t st, bool defer_ops = false) {
     }
     e->any_noise = e->noise_count > 0;
   }
-  if (!e->ops.empty() && !(defer_ops && e->bins.empty() && !(e->cfg.flags & SKB_CFG_NO_BATCH))) {
+  if (!e->ops.empty() && !(defer_ops && bins_batch_ok(e) && !(e->cfg.flags & SKB_CFG_NO_BATCH))) {
     /* keep per-voice order: stable sort by slot, then one run per slot */
     std::vector<skb_op> &ops = e->ops;
     size_t cnt = 0;
@@ -878,50 +973,7 @@ static int sync_inputs(skb_engine *e, cudaStream_t st, bool defer_ops = false) {
   return SKB_OK;
 }
 
-/* ---- exchange step: NCCL reduce of the partial mixes (SURVEY 8e) ------------------------------- */
-/* libnccl.so.2 is opened on first use: a single-GPU host never needs it.  In a process that already
- * holds an NCCL (torch's bundled copy) the loader hands back that one. */
-struct NcclApi {
-  void *h = nullptr;
-  bool tried = false;
-  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
-  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
-  ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
-  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-  ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*GroupStart)() = nullptr;
-  ncclResult_t (*GroupEnd)() = nullptr;
-  const char *(*GetErrorString)(ncclResult_t) = nullptr;
-};
-static NcclApi g_nccl;
-
-static bool nccl_load() {
-  if (g_nccl.tried) return g_nccl.h != nullptr;
-  g_nccl.tried = true;
-  const char *names[] = {getenv("SKB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
-  void *h = nullptr;
-  for (int i = 0; i < 3 && !h; i++) if (names[i] && names[i][0]) h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
-  if (!h) return false;
-#define SKB_NCCL_SYM(field, name) *(void **)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) { dlclose(h); return false; }
-  SKB_NCCL_SYM(GetUniqueId, "ncclGetUniqueId") SKB_NCCL_SYM(CommInitRank, "ncclCommInitRank")
-  SKB_NCCL_SYM(CommInitAll, "ncclCommInitAll") SKB_NCCL_SYM(CommDestroy, "ncclCommDestroy")
-  SKB_NCCL_SYM(Reduce, "ncclReduce") SKB_NCCL_SYM(Broadcast, "ncclBroadcast")
-  SKB_NCCL_SYM(Send, "ncclSend") SKB_NCCL_SYM(Recv, "ncclRecv")
-  SKB_NCCL_SYM(GroupStart, "ncclGroupStart") SKB_NCCL_SYM(GroupEnd, "ncclGroupEnd") SKB_NCCL_SYM(GetErrorString, "ncclGetErrorString")
-#undef SKB_NCCL_SYM
-  g_nccl.h = h;
-  return true;
-}
-
-#define NK(call)                                                                                   \
-  do {                                                                                             \
-    ncclResult_t _r = (call);                                                                      \
-    if (_r != ncclSuccess) return fail(e, SKB_ERR_CUDA, #call, g_nccl.GetErrorString(_r));          \
-  } while (0)
-
+/* ---- exchange step: the skb_comm_* entry points (NCCL loader and NK() are defined near the top) ---- */
 int skb_comm_unique_id(void *id_out) {
   if (!id_out) return SKB_ERR_ARG;
   if (!nccl_load()) return SKB_ERR_STATE;
@@ -1068,8 +1120,9 @@ static int batch_launch(skb_engine *e) {
   const std::vector<int> &cta_of = wide ? e->cta_of_row_wide : e->cta_of_row;
   const int ncta = rows ? e->n_free_rows : std::max(e->free_ctas, 1);
   const int n_free_pad = e->n_free_pad;
-  auto cta_of_slot = [&cta_of, n_free_pad, rows](int slot) {
-    return (slot >= 0 && slot < n_free_pad) ? (rows ? (slot >> 5) : cta_of[(size_t)(slot >> 5)]) : 0; };
+  const int nbk = ncta + 1;                                  /* op buckets: the CTAs (rows) of the free kernel, then the bins */
+  auto cta_of_slot = [&cta_of, n_free_pad, rows, ncta](int slot) {
+    return (slot >= 0 && slot < n_free_pad) ? (rows ? (slot >> 5) : cta_of[(size_t)(slot >> 5)]) : ncta; };
   for (size_t i = 0; i < nops; i++) e->batch.ops[i]._pad = cta_of_slot(e->batch.ops[i].voice);   /* bucket key; the kernel ignores it */
   cudaError_t r;
   if (wait_staging(e)) return e->err;
@@ -1077,7 +1130,7 @@ static int batch_launch(skb_engine *e) {
    * H2D on a COPY stream, double buffered: while launch k renders, the host stages and uploads launch k + 1,
    * and the render stream only waits on an event that has long fired (three dependent copies on the render
    * stream cost ~15-20 us of a 0.4 ms step). */
-  const size_t nwi = (size_t)nwin + (size_t)nwin * (ncta + 1);
+  const size_t nwi = (size_t)nwin + (size_t)nwin * (nbk + 1);
   const size_t nw = nops ? ((size_t)e->cap + 31) / 32 : 0;
   const size_t off_ops = (nwi * sizeof(int) + 15) & ~(size_t)15;
   const size_t off_wake = off_ops + nops * sizeof(skb_op);
@@ -1094,20 +1147,20 @@ static int batch_launch(skb_engine *e) {
   {
     /* counting sort of every boundary's ops by CTA straight into the staging block (stable: queue order within
      * a voice survives), then by slot inside the few-op buckets; the bucket starts are the CSR rows */
-    int *csr = (int *)hs + nwin;                              /* [nwin][ncta + 1] */
+    int *csr = (int *)hs + nwin;                              /* [nwin][nbk + 1] */
     skb_op *outp = (skb_op *)(hs + off_ops);
-    e->sort_cursor.assign((size_t)ncta + 1, 0);
+    e->sort_cursor.assign((size_t)nbk + 1, 0);
     int *cur = e->sort_cursor.data();
     for (int w = 0; w < nwin; w++) {
-      int *row = csr + (size_t)w * (ncta + 1);
+      int *row = csr + (size_t)w * (nbk + 1);
       const int b = e->batch.win_ob[w], en = e->batch.win_ob[w + 1];
-      for (int c = 0; c <= ncta; c++) cur[c] = 0;
+      for (int c = 0; c <= nbk; c++) cur[c] = 0;
       for (int i = b; i < en; i++) cur[e->batch.ops[i]._pad]++;
       int pos = b;
-      for (int c = 0; c < ncta; c++) { row[c] = pos; pos += cur[c]; cur[c] = row[c]; }
-      row[ncta] = en;
+      for (int c = 0; c < nbk; c++) { row[c] = pos; pos += cur[c]; cur[c] = row[c]; }
+      row[nbk] = en;
       for (int i = b; i < en; i++) outp[cur[e->batch.ops[i]._pad]++] = e->batch.ops[i];
-      for (int c = 0; c < ncta; c++) {
+      for (int c = 0; c < nbk; c++) {
         const int s0 = row[c], s1 = row[c + 1];
         for (int i = s0 + 1; i < s1; i++) {                   /* insertion sort by slot, stable */
           const skb_op key = outp[i];
@@ -1166,7 +1219,7 @@ static int batch_launch(skb_engine *e) {
     fa.cta_rowlist = wide ? e->d_lists + e->list_a_wide.off : e->d_ctarows; fa.rows_cap = e->rows_cap;
     fa.tables = e->d_tables; fa.noise = e->d_noise;
     fa.nframes = nframes; fa.ssc_before = (unsigned long long)e->batch.ssc0;
-    fa.win_frames = d_winp; fa.win_ob = d_winp + nwin; fa.nwin = nwin; fa.ob_stride = ncta + 1;
+    fa.win_frames = d_winp; fa.win_ob = d_winp + nwin; fa.nwin = nwin; fa.ob_stride = nbk + 1;
     fa.bops = d_bopsp; fa.wake = d_wake;
     fa.ctarows = e->d_partials; fa.row_stride = nframes;
     fa.envbuf = e->d_envbuf; fa.counters = e->d_counters; fa.cta_phase = e->d_ctaphase;
@@ -1206,10 +1259,21 @@ static int batch_launch(skb_engine *e) {
       e->wide_timing_pending = true;
     }
   }
-  if (!e->bins.empty()) {                                     /* (a batch with bins is always one segment without in-kernel ops) */
+  if (e->n_small_bins > 0) {                                  /* one warp per bin, boundary ops applied in-kernel */
+    BinWarpArgs ba;
+    memset(&ba, 0, sizeof(ba));
+    ba.pq = e->d_pq; ba.sq = e->d_sq[e->cur]; ba.cap = e->cap; ba.bins = e->d_bins; ba.nbins = e->n_small_bins;
+    ba.tables = e->d_tables; ba.noise = e->d_noise; ba.nframes = nframes; ba.ssc_before = (unsigned long long)e->batch.ssc0;
+    ba.win_frames = d_winp; ba.win_ob = d_winp + nwin; ba.nwin = nwin; ba.ob_stride = nbk + 1; ba.ob_bucket = ncta;
+    ba.bops = d_bopsp; ba.partials = e->d_partials; ba.row_stride = nframes; ba.counter = e->d_counters + 1;
+    ba.tap = e->tap_on ? e->d_tap + (size_t)e->batch.tap_frame0 * e->n : nullptr; ba.voice_of_slot = e->d_vos; ba.tap_n = e->tap_on ? e->n : 0;
+    k_render_bins_warp<<<(e->n_small_bins + SKB_BINW_WARPS - 1) / SKB_BINW_WARPS, SKB_BINW_WARPS * 32, 0, st>>>(ba);
+    e->stats.kernel_launches++;
+  }
+  if ((int)e->bins.size() > e->n_small_bins) {                /* big components: one CTA each, one launch per callback, ops by k_apply_ops */
     const int nt = e->max_bin_threads;
     const size_t smem = (size_t)3 * nt * sizeof(float) + (size_t)2 * (nt / 32) * sizeof(float2);
-    k_render_bins<<<(int)e->bins.size(), nt, smem, st>>>(e->d_pq, e->d_sq[e->cur], e->cap, e->d_bins, e->d_tables,
+    k_render_bins<<<(int)e->bins.size() - e->n_small_bins, nt, smem, st>>>(e->d_pq, e->d_sq[e->cur], e->cap, e->d_bins + e->n_small_bins, e->d_tables,
                                                          e->d_noise, nframes, (unsigned long long)e->batch.ssc0,
                                                          e->d_partials, nframes, e->d_counters + 1,
                                                          e->tap_on ? e->d_tap + (size_t)e->batch.tap_frame0 * e->n : nullptr, e->d_vos,
@@ -1257,7 +1321,7 @@ int skb_render_mix(skb_engine *e, int nframes, uint64_t ssc_before, const float 
    * re-plans and modulation bins end the batch. */
   bool extend = e->batch.open && e->batch.st == st && e->batch.mix + (size_t)e->batch.frames * 2 == d_mix &&
                 e->batch.ssc0 + (uint64_t)e->batch.frames == ssc_before &&
-                e->batch.frames + nframes <= e->cfg.max_frames && e->bins.empty() && e->planned && !e->need_plan &&
+                e->batch.frames + nframes <= e->cfg.max_frames && bins_batch_ok(e) && e->planned && !e->need_plan &&
                 e->dirty_list.empty() && !(e->cfg.flags & SKB_CFG_NO_BATCH);
   if (extend && !e->ops.empty() && e->batch.frames % SKB_ENV_WIN != 0) extend = false;   /* (boundaries are window starts) */
   if (!extend) {
@@ -1300,7 +1364,7 @@ int skb_render_mix(skb_engine *e, int nframes, uint64_t ssc_before, const float 
   e->batch.frames += nframes;
   if (e->tap_on) e->tap_cursor += nframes;
   e->stats.frames_rendered += (uint64_t)nframes;
-  if (!e->bins.empty() || (e->cfg.flags & SKB_CFG_NO_BATCH)) return batch_launch(e);
+  if (!bins_batch_ok(e) || (e->cfg.flags & SKB_CFG_NO_BATCH)) return batch_launch(e);
   return e->err;
 }
 

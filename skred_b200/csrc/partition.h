@@ -83,6 +83,37 @@ static inline void skb_partition(const int32_t *comp, int n_voices, int world, i
   free(csize);
 }
 
+/* The same with a memory: `prev` (or NULL) is the owner map of the previous plan.  A component whose voices all had
+ * one owner keeps it; a component that MERGED voices of several owners goes to the rank that held most of them (ties ->
+ * lowest rank), so only the smaller side has to move; a component that split keeps its voices where they were.
+ * Modulation routing can therefore change after rendering has started without reshuffling unrelated voices (the greedy
+ * map above re-deals every later component when an early one changes size).  Deterministic on every rank. */
+static inline void skb_partition_stable(const int32_t *comp, int n_voices, int world, const int32_t *prev, int32_t *owner) {
+  if (!prev || world <= 1) { skb_partition(comp, n_voices, world, owner); return; }
+  int32_t *votes = (int32_t *)calloc((size_t)n_voices, sizeof(int32_t));   /* votes of the component's best rank so far */
+  int32_t *best = (int32_t *)malloc((size_t)n_voices * sizeof(int32_t));
+  int32_t *cnt = (int32_t *)calloc((size_t)world, sizeof(int32_t));
+  for (int v = 0; v < n_voices; v++) best[v] = -1;
+  /* per component: count its voices per previous owner; components are visited root by root */
+  int32_t *next = (int32_t *)malloc((size_t)n_voices * sizeof(int32_t));   /* linked list of a component's voices */
+  int32_t *head = (int32_t *)malloc((size_t)n_voices * sizeof(int32_t));
+  for (int v = 0; v < n_voices; v++) head[v] = -1;
+  for (int v = n_voices - 1; v >= 0; v--) { next[v] = head[comp[v]]; head[comp[v]] = v; }
+  for (int r = 0; r < n_voices; r++) {
+    if (comp[r] != r) continue;
+    for (int w = 0; w < world; w++) cnt[w] = 0;
+    for (int v = head[r]; v >= 0; v = next[v]) {
+      const int o = prev[v];
+      if (o >= 0 && o < world) cnt[o]++;
+    }
+    int b = 0;
+    for (int w = 1; w < world; w++) if (cnt[w] > cnt[b]) b = w;
+    best[r] = b;
+  }
+  for (int v = 0; v < n_voices; v++) owner[v] = best[comp[v]];
+  free(votes); free(best); free(cnt); free(next); free(head);
+}
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,8 +28,12 @@
  */
 #pragma once
 
+#ifndef RP_FB
 #define RP_FB 32                       /* frames per block */
+#endif
+#ifndef RP_G
 #define RP_G 4                         /* gather warps; each takes RP_FB / RP_G frames of a block */
+#endif
 #define RP_WARPS (RP_G + 2)
 #define RP_THREADS (RP_WARPS * 32)
 #define RP_NBUF 4                      /* blocks in flight: t (A), t-1 (G), t-2 (C), t-3 (mix) */
@@ -46,6 +50,8 @@ struct RowSmem {
   int bslow[RP_NBUF];                  /* some lane's one-shot ends inside the block */
   float2 pan[32];
   int envover[32];                     /* the lane's envelope ended at a rendered frame of this segment (synth.c:429) */
+  EnvRec er[32];                       /* envelope records of the lanes on a time-varying segment */
+  unsigned varmask;                    /* ... and which lanes those are */
   float fphase[32];
   float2 gtile[SKB_TILE_FLOAT2];       /* generic rows: stereo tile and 16 frames of row */
   float2 grow[SKB_UNIT];
@@ -67,12 +73,24 @@ __device__ __forceinline__ void rp_phase_block(RowSmem &S, int bi, int nf, const
     }
     if (H >= nf) {
       float phase = fs.phase;
-#pragma unroll 8
-      for (int j = 0; j < nf; j++) {
-        const float q = phase + c.inc;                                /* :226 */
-        const float w = q - c.hi_wrap;                                /* :247 (exact, see stage_phase) */
+      int j = 0;
+      for (; j + 8 <= nf; j += 8) {
+        float p8[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const float q = phase + c.inc;                              /* :226 */
+          const float w = q - c.hi_wrap;                              /* :247 (exact, see stage_phase) */
+          phase = (q >= c.hi_wrap) ? w : q;
+          p8[k] = phase;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) ph[j + k][lane] = p8[k];          /* :258 */
+      }
+      for (; j < nf; j++) {
+        const float q = phase + c.inc;
+        const float w = q - c.hi_wrap;
         phase = (q >= c.hi_wrap) ? w : q;
-        ph[j][lane] = phase;                                          /* :258 */
+        ph[j][lane] = phase;
       }
       fs.phase = phase;
       nv = nf;
@@ -93,63 +111,120 @@ __device__ __forceinline__ void rp_phase_block(RowSmem &S, int bi, int nf, const
   if (ended) dead = true;
 }
 
-/* G: table reads and envelope gains of frames [j0, j1) of one block */
-__device__ __forceinline__ void rp_gather_block(RowSmem &S, int bi, int j0, int j1, int frame0, const FastK &c, bool varying,
-                                                const EnvRec &er, int lane, const float *__restrict__ tables) {
-  float x[RP_FB / RP_G];
+/* G: table reads of RP_FB / RP_G frames of one block, branch-free: the phases of all frames are loaded first, then the
+ * indices, then the table words, so the loads of the frames overlap.  Frames past the end of a ragged block hold a
+ * stale phase: the index is clamped into the table, the value is never used.
+ * CZ: 0 none (the index is the truncated phase), 1 the lane's piecewise / fast_pow form (frame_x). */
+template <int CZ>
+__device__ __forceinline__ void rp_gather_block(RowSmem &S, int bi, int j0, const FastK &c, int lane,
+                                                const float *__restrict__ tables) {
+  constexpr int NF = RP_FB / RP_G;
+  float q[NF], x[NF];
+  unsigned idx[NF];
 #pragma unroll
-  for (int k = 0; k < RP_FB / RP_G; k++) {
-    const int j = j0 + k;
-    x[k] = (j < j1) ? frame_x(c, S.ph[bi][j][lane], tables) : 0.0f;   /* :262-274 */
+  for (int k = 0; k < NF; k++) q[k] = S.ph[bi][j0 + k][lane];
+#pragma unroll
+  for (int k = 0; k < NF; k++) {
+    if (CZ == 0) {
+      idx[k] = min(trunc_small_u(q[k]), (unsigned)c.imax);           /* :268 */
+    } else {
+      const float u = q[k] * c.inv_size;                              /* :151 */
+      const float r = c.is_pow ? dev_fast_pow(u, c.k1) : ((u < c.czT) ? u * c.k1 : c.czC + (u - c.czU) * c.k2);
+      idx[k] = (unsigned)max(min(c_f2i(r * c.size_f), c.imax), 0);    /* :214, 265, 271-272 */
+    }
   }
 #pragma unroll
-  for (int k = 0; k < RP_FB / RP_G; k++) if (j0 + k < j1) S.xs[bi][j0 + k][lane] = x[k];
-  if (varying) {
-    const int nv = S.nval[bi][lane] & (RP_ENDED - 1);
-    for (int j = j0; j < j1 && j < nv; j++) {
+  for (int k = 0; k < NF; k++) x[k] = __ldg(c.tp + idx[k]);           /* :274 */
+#pragma unroll
+  for (int k = 0; k < NF; k++) S.xs[bi][j0 + k][lane] = x[k];
+}
+
+/* G: envelope gains amp * (amp_envelope_step() * velocity) of one block (synth.c:398-431, 582, 588), FRAME-PARALLEL: the
+ * envelope is a closed form of the sample counter, so thread (q, f) evaluates frame f of the q-th lane that sits on a
+ * time-varying segment — the IEEE divisions cost (varying lanes x frames) / 128 threads, not 8 frames x a whole warp. */
+__device__ __forceinline__ void rp_env_block(RowSmem &S, int bi, int nf, int frame0, int gtid) {
+  const unsigned mask = S.varmask;
+  const int items = __popc(mask) * nf;
+  for (int i = gtid; i < items; i += RP_G * 32) {
+    const int q = i / nf, f = i - q * nf;
+    const int v = __fns(mask, 0, q + 1);                              /* the q-th varying lane */
+    if (f < (S.nval[bi][v] & (RP_ENDED - 1))) {
+      const EnvRec r = S.er[v];
       bool done;
-      S.gv[bi][j][lane] = env_gain_at(er, er.t0 + frame0 + j + 1, er.tr0 + frame0 + j + 1, &done);   /* :398-431, 582, 588 */
-      if (done) S.envover[lane] = 1;                                  /* :429 */
+      S.gv[bi][f][v] = env_gain_at(r, r.t0 + frame0 + f + 1, r.tr0 + frame0 + f + 1, &done);
+      if (done) S.envover[v] = 1;                                     /* :429 */
     }
   }
 }
 
-/* G: pan, sum over the row's 32 voices, partial row -> HBM.  Lane (f, h), f = lane % 8, h = lane / 8, adds voices
- * 8h .. 8h+7 of frame j0 + f left to right, the four groups are joined by two shuffles: a fixed order. */
+/* G: pan, sum over the row's 32 voices, partial row -> HBM.  Lane (f, h), f = lane % FPW, h = lane / FPW, adds voices
+ * VPG h .. VPG h + VPG - 1 of frame j0 + f left to right, the lane groups are joined by shuffles: a fixed order. */
 __device__ __forceinline__ void rp_mix_block(const RowSmem &S, int bi, int j0, int nf, float2 *orow_at, int lane) {
-  const int f = lane & 7, h = lane >> 3, j = j0 + f;
+  constexpr int FPW = RP_FB / RP_G;              /* frames per gather warp */
+  constexpr int NV = 32 / FPW * 0 + (32 * FPW / 32) * 0 + (32 / (32 / FPW));   /* = FPW ... voices per lane group: 32 / (32 / FPW) */
+  static_assert(FPW == 4 || FPW == 8 || FPW == 16, "RP_FB / RP_G must be 4, 8 or 16");
+  constexpr int NG = 32 / FPW;                   /* lane groups; each adds 32 / NG voices */
+  constexpr int VPG = 32 / NG;
+  (void)NV;
+  const int f = lane % FPW, h = lane / FPW, j = j0 + f;
   float L = 0.0f, R = 0.0f;
   if (j < nf) {
 #pragma unroll
-    for (int v = 0; v < 8; v++) {
-      const float2 p = S.pan[8 * h + v];
-      const float o = S.out[bi][j][8 * h + v];
+    for (int v = 0; v < VPG; v++) {
+      const float2 p = S.pan[VPG * h + v];
+      const float o = S.out[bi][j][VPG * h + v];
       L += o * p.x; R += o * p.y;                                     /* :603-606 */
     }
   }
 #pragma unroll
-  for (int d = 8; d < 32; d <<= 1) { L += __shfl_xor_sync(0xffffffffu, L, d); R += __shfl_xor_sync(0xffffffffu, R, d); }
+  for (int d = FPW; d < 32; d <<= 1) { L += __shfl_xor_sync(0xffffffffu, L, d); R += __shfl_xor_sync(0xffffffffu, R, d); }
   if (h == 0 && j < nf) orow_at[j] = make_float2(L, R);
 }
 
-/* C: biquad, smoother, voice_sample of one block in which no lane ends */
+/* C: biquad, smoother, voice_sample of one block in which no lane ends.  The inputs of 8 frames are loaded into
+ * registers BEFORE any of their results is stored: left to itself the compiler keeps every shared-memory load behind
+ * the store of the frame before (it cannot tell the arrays of RowSmem apart once the block index is dynamic), which
+ * puts the 30-cycle load latency on the chain of every frame (measured: 51 cycles per frame for a plain voice). */
 template <int FILT, int DYN>
 __device__ __forceinline__ void rp_out_block(RowSmem &S, int bi, int nf, const FastK &c, FastS &s, int lane) {
   float x1 = s.x1, x2 = s.x2, y1 = s.y1, y2 = s.y2, g = s.g, last = s.sample;
-#pragma unroll 8
-  for (int j = 0; j < nf; j++) {
-    float v = S.xs[bi][j][lane];
-    if (FILT) {                                                       /* :349-364 */
-      const float y = c.b0 * v + c.b1 * x1 + c.b2 * x2 - c.a1 * y1 - c.a2 * y2;
-      x2 = x1; x1 = v; y2 = y1; y1 = y;
-      v = (FILT == 2 && !c.has_f) ? v : y;
-    }
+  const float *xs = &S.xs[bi][0][lane];
+  const float *gv = &S.gv[bi][0][lane];
+  float *out = &S.out[bi][0][lane];
+  int j = 0;
+  for (; j + 8 <= nf; j += 8) {
+    float v[8], gn[8], o[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = xs[(j + k) * 32];
     if (DYN) {
-      const float gain = c.is_buf ? S.gv[bi][j][lane] : c.gc;         /* :580-588 */
-      g = g + c.sm_k * (gain - g);                                    /* :589-592 */
+#pragma unroll
+      for (int k = 0; k < 8; k++) gn[k] = c.is_buf ? gv[(j + k) * 32] : c.gc;     /* :580-588 */
     }
-    last = v * g;                                                     /* :593 */
-    S.out[bi][j][lane] = last;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      float w = v[k];
+      if (FILT) {                                                     /* :349-364 */
+        const float y = c.b0 * w + c.b1 * x1 + c.b2 * x2 - c.a1 * y1 - c.a2 * y2;
+        x2 = x1; x1 = w; y2 = y1; y1 = y;
+        w = (FILT == 2 && !c.has_f) ? w : y;
+      }
+      if (DYN) g = g + c.sm_k * (gn[k] - g);                          /* :589-592 */
+      o[k] = w * g;                                                   /* :593 */
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) out[(j + k) * RP_OSTRIDE] = o[k];
+    last = o[7];
+  }
+  for (; j < nf; j++) {
+    float w = xs[j * 32];
+    if (FILT) {
+      const float y = c.b0 * w + c.b1 * x1 + c.b2 * x2 - c.a1 * y1 - c.a2 * y2;
+      x2 = x1; x1 = w; y2 = y1; y1 = y;
+      w = (FILT == 2 && !c.has_f) ? w : y;
+    }
+    if (DYN) { const float gain = c.is_buf ? gv[j * 32] : c.gc; g = g + c.sm_k * (gain - g); }
+    last = w * g;
+    out[j * RP_OSTRIDE] = last;
   }
   if (FILT) { s.x1 = x1; s.x2 = x2; s.y1 = y1; s.y2 = y2; }
   s.g = g; s.sample = last;
@@ -275,15 +350,20 @@ __global__ void __launch_bounds__(RP_THREADS) k_render_rows(const __grid_constan
       if (roleC) {
         S.pan[lane] = make_float2(c.panL, c.panR);
         S.envover[lane] = 0;
+        if (varying) S.er[lane] = er;
+        const unsigned vm = __ballot_sync(0xffffffffu, varying);
+        if (lane == 0) S.varmask = vm;
         const bool st = !varying && (fs.g + c.sm_k * (c.gc - fs.g) == fs.g);     /* smoother on its fixed point: not stepped */
         dyn = !__all_sync(0xffffffffu, st);
         const bool anyf = __any_sync(0xffffffffu, c.has_f), allf = __all_sync(0xffffffffu, c.has_f || dead);
         filt = !anyf ? 0 : (allf ? 1 : 2);
       }
       const bool has_rows = __any_sync(0xffffffffu, varying);
+      const bool cz_any = __any_sync(0xffffffffu, !dead && c.czT != CUDART_INF_F);   /* some lane warps its phase (cz_setup) */
       const int nb = (nfr + RP_FB - 1) / RP_FB;
       __syncthreads();
       for (int t = 0; t < nb + 3; t++) {
+        const long long t_s0 = clock64();
         if (roleA) {
           if (t < nb) rp_phase_block(S, t & (RP_NBUF - 1), min(RP_FB, nfr - t * RP_FB), c, fs, dead, lane);
         } else if (roleG) {
@@ -292,7 +372,9 @@ __global__ void __launch_bounds__(RP_THREADS) k_render_rows(const __grid_constan
           if (bg >= 0 && bg < nb) {
             const int nf = min(RP_FB, nfr - bg * RP_FB);
             const int j0 = g * (RP_FB / RP_G);
-            rp_gather_block(S, bg & (RP_NBUF - 1), j0, min(j0 + RP_FB / RP_G, nf), bg * RP_FB, c, varying, er, lane, tables);
+            if (cz_any) rp_gather_block<1>(S, bg & (RP_NBUF - 1), j0, c, lane, tables);
+            else rp_gather_block<0>(S, bg & (RP_NBUF - 1), j0, c, lane, tables);
+            if (has_rows) rp_env_block(S, bg & (RP_NBUF - 1), nf, bg * RP_FB, g * 32 + lane);
           }
           if (bm >= 0 && bm < nb)
             rp_mix_block(S, bm & (RP_NBUF - 1), g * (RP_FB / RP_G), min(RP_FB, nfr - bm * RP_FB), orow + f0 + bm * RP_FB, lane);
@@ -344,7 +426,13 @@ __global__ void __launch_bounds__(RP_THREADS) k_render_rows(const __grid_constan
             }
           }
         }
+        const long long t_s1 = clock64();
         __syncthreads();
+        if (lane == 0 && (warp == 0 || warp == 1 || roleC)) {      /* diagnostics (skb_stats.phase_cycles): work and wait per stage */
+          const int k = roleA ? 0 : (roleC ? 2 : 1);
+          atomicAdd(a.counters + 10 + k, (unsigned long long)(t_s1 - t_s0));
+          atomicAdd(a.counters + 13 + k, (unsigned long long)(clock64() - t_s1));
+        }
       }
       /* ---- registers -> HBM record ---- */
       if (roleA) S.fphase[lane] = fs.phase;

@@ -691,6 +691,9 @@ int skb_shim_snapshot_range(int first, int n) {
   if (r == SKB_OK) {
     for (int k = 0; k < n; k++) {
       const int v = first + k;
+      /* a voice-sharded engine holds the evolving state of ITS voices only: the mirror of a voice another GPU owns is
+       * left as it is (what the setters last wrote) instead of being overwritten with the zeros skb_snapshot returns */
+      if (g_cfg_world > 1 && !skb_owns_voice(g_engine, v)) continue;
       voice_phase[v] = st[k].phase;
       voice_finished[v] = st[k].finished;
       voice_sample[v] = st[k].sample;

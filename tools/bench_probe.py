@@ -38,9 +38,12 @@ for k in range(N):
               (k, st.last_render_ms, st.last_wide_ms[0], st.last_wide_ms[1], st.last_wide_ms[2], act, cr), flush=True)
     if k == N - 1:
         nb = st.cta_batches - base.cta_batches
+        if st.rows_launches:
+            print("   k_render_rows us/CTA since launch 16 [A work, G work, C work, A wait, G wait, C wait]:",
+                  ["%.1f" % ((a - b) / max(nb, 1) / 1965.0) for a, b in zip(st.phase_cycles[:6], base.phase_cycles[:6])])
         print("   phase us/CTA-pass [compact setup tables prepass render wait rowsum store] since launch 16:",
               ["%.1f" % ((a - b) / max(nb, 1) / 1965.0) for a, b in zip(st.phase_cycles, base.phase_cycles)])
-    if k == 15:
+    if k == min(15, N - 3):
         base = st
     prev = st
 

@@ -38,7 +38,7 @@ only = sys.argv[3].split(",") if len(sys.argv) > 3 else None
 for name, fn in CLASSES.items():
     if only and name not in only:
         continue
-    sk = Skred(V, private=True, max_frames=max(F, 512))
+    sk = Skred(V, private=True, max_frames=max(F, 512), rank=0, world=int(os.environ.get("SKB_CB_WORLD", "1")))
     from skred_b200.host import install_table
     for i, k in enumerate(("sine_lutable_0", "triangle_lutable_0", "impulse_lutable_0")):
         install_table(sk, 200 + i, luts[k])
@@ -51,7 +51,7 @@ for name, fn in CLASSES.items():
     for it in range(12):          # 12 blocks: past attack (441 frames) after ~1, decay (4410) after ~10
         sk.lib.synth(out.ctypes.data, None, F, 2, None)
         ms.append(sk.stats().last_render_ms)
-    vs = V * F
+    vs = V // int(os.environ.get("SKB_CB_WORLD", "1")) * F
     st_ = sk.stats()
     print("   phase us/CTA-pass [compact setup tables prepass render wait rowsum store]:",
           ["%.1f" % (x / max(st_.cta_batches, 1) / 1965.0) for x in st_.phase_cycles])
