@@ -290,7 +290,8 @@ def own_arm(a):
 
     sk = Skred(V, device=local, rank=rank, world=world, max_frames=max(F, 512))
     # steps this arm renders: (W + R*K) device-resident, 3 kernel-alone, K with the L2 flushed, W + K end to end, latency blocks
-    reps_guess = max(1, min(40, int(np.ceil(a.min_timed_s / max(a.steps * 0.7e-3 * F / 8192.0, 1e-6))))) if a.min_timed_s > 0 else 1
+    # repetitions needed if a step took only 0.4 ms (the fastest it gets, 8 GPUs): the event horizon is sized for them
+    reps_guess = max(1, min(64, int(np.ceil(a.min_timed_s / max(a.steps * 0.4e-3 * F / 8192.0, 1e-6))))) if a.min_timed_s > 0 else 1
     total_frames = (2 * a.warmup + (2 * reps_guess + 4) * a.steps + 8) * F + (a.latency_blocks + 64) * 512
     wl = W.config5(V, seconds=600.0, luts=load_luts(), event_seconds=total_frames / SR + 1.0, stationary=True)
     W.install(sk, wl)
@@ -429,7 +430,7 @@ def own_arm(a):
         spent = sum(r[0] for r in reps) * 1e-3
         if world > 1:
             spent = max_over_ranks(spent)                 # every rank must take the same decision
-        if spent >= a.min_timed_s or len(reps) >= reps_guess + 1 or len(reps) >= 40:
+        if spent >= a.min_timed_s or len(reps) >= reps_guess:
             break
     order = sorted(range(len(reps)), key=lambda i: reps[i][0])
     dev_ms, act_dev, launches = reps[order[len(order) // 2]]
