@@ -61,7 +61,7 @@ def shim_so(v):
 
 
 def build_engine(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "voice_kernels.cuh", "free_kernel.cuh", "row_kernel.cuh", "partition.h")] + [
+    srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "voice_kernels.cuh", "free_kernel.cuh", "row_kernel.cuh", "level_kernel.cuh", "partition.h")] + [
         os.path.join(INC, "skred_b200.h"), __file__]
     if not force and newer(ENGINE_SO, srcs):
         return ENGINE_SO

@@ -60,6 +60,12 @@ struct skb_engine {
 
   /* plan */
   std::vector<int32_t> comp, owner, slot_of_voice, voice_of_slot, level;
+  /* levelled modulated voices (level_kernel.cuh): components whose modulation graph is a DAG */
+  std::vector<int32_t> lev_of, trace_of;            /* per voice: level (-1 = not levelled), trace row (-1 = nobody reads it) */
+  std::vector<std::vector<int32_t>> lev_deps;       /* per voice: the levelled voices that read it */
+  std::vector<std::pair<int, int>> lev_rows;        /* per level: (first row of 32 slots, rows) */
+  int n_lev_pad = 0, n_lev_rows = 0, n_traces = 0;  /* slots [n_free_pad, n_lev_pad) hold the levelled voices */
+  float *d_trace = nullptr; size_t trace_cap = 0;   /* [n_traces][max_frames + 1] */
   std::vector<int32_t> bin_of_voice;                /* -1 = free */
   std::vector<skb_bin_desc> bins;
   std::vector<uint64_t> edge_sig;                   /* per voice: hash of its live edges (re-plan trigger) */
@@ -284,6 +290,7 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
   e->noise_flag.assign(n, 0);
   e->comp.assign(n, 0); e->owner.assign(n, 0); e->slot_of_voice.assign(n, -1);
   e->level.assign(n, 0); e->bin_of_voice.assign(n, -1); e->edge_sig.assign(n, 0);
+  e->lev_of.assign(n, -1); e->trace_of.assign(n, -1); e->lev_deps.assign(n, std::vector<int32_t>());
   bool ok = cudaSetDevice(cfg->device) == cudaSuccess &&
             cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_h2d, cudaEventDisableTiming) == cudaSuccess &&
@@ -318,6 +325,8 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
                                  (int)skb_free_smem_bytes()) == cudaSuccess &&
             cudaFuncSetAttribute(k_render_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)skb_rows_smem_bytes()) == cudaSuccess &&
+            cudaFuncSetAttribute(k_render_levels, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)skb_levels_smem_bytes()) == cudaSuccess &&
             cudaMallocHost((void **)&e->h_gain, (size_t)mf * sizeof(float)) == cudaSuccess &&
             cudaMallocHost((void **)&e->h_noise, (size_t)mf * sizeof(float)) == cudaSuccess &&
             cudaMallocHost((void **)&e->h_out, (size_t)mf * sizeof(float2)) == cudaSuccess &&
@@ -344,7 +353,7 @@ void skb_destroy(skb_engine *e) {
   batch_launch(e);
   if (e->stream) cudaStreamSynchronize(e->stream);
   skb_comm_destroy(e);
-  cudaFree(e->d_gather); cudaFree(e->d_mig); cudaFree(e->d_migidx);
+  cudaFree(e->d_gather); cudaFree(e->d_mig); cudaFree(e->d_migidx); cudaFree(e->d_trace);
   cudaFree(e->d_pq); cudaFree(e->d_sq[0]); cudaFree(e->d_sq[1]); cudaFree(e->d_tables);
   cudaFree(e->d_bins); cudaFree(e->d_partials); cudaFree(e->d_mix); cudaFree(e->d_out);
   cudaFree(e->d_gain); cudaFree(e->d_noise); cudaFree(e->d_idx); cudaFree(e->d_recs);
@@ -459,6 +468,11 @@ static int make_ref(const skb_engine *e, int v, int m, bool none_if_negative) {
   if (m < 0) return none_if_negative ? SKB_REF_NONE : SKB_REF_ZERO;
   if (m >= e->n) return SKB_REF_ZERO;
   if (m == v) return SKB_REF_SELF;
+  if (e->lev_of[v] >= 0) {
+    /* a levelled voice reads its modulator's trace: current frame if the modulator comes first in the voice loop */
+    if (e->lev_of[m] < 0 || e->trace_of[m] < 0) return SKB_REF_ZERO;    /* cannot happen for a live edge */
+    return SKB_REF_TRACE | e->trace_of[m] | (m < v ? SKB_REF_CUR : 0);
+  }
   const int b = e->bin_of_voice[v];
   if (b < 0 || e->bin_of_voice[m] != b) return SKB_REF_ZERO;   /* cannot happen for a live edge */
   const int l = e->slot_of_voice[m] - e->bins[b].slot0;
@@ -496,11 +510,37 @@ static void pack_record(const skb_engine *e, int v, float4 *r) {
   r[5] = make_float4(p.a2, p.env_attack, p.env_decay, p.env_sustain);
   r[6] = make_float4(p.env_release, p.amp_mod_depth, p.smoother_k, p.pan_mod_depth);
   r[7] = make_float4(fi(p.filter_mode), fi(am_ref), fi(pm_ref), fi(e->level[v]));
+  /* levelled voice: its FM modulator's phase increment (synth.c:553 reads voice_phase_inc[mod] at render time) and the
+   * trace row its own voice_sample goes to (+ 1: a cleared record means none) */
+  const float fm_minc = (e->lev_of[v] >= 0 && live[0] >= 0) ? e->par[live[0]].phase_inc : 0.0f;
+  r[8] = make_float4(fm_minc, fi(e->lev_of[v] >= 0 ? e->trace_of[v] + 1 : 0), 0.0f, 0.0f);
 }
 
 static int wait_staging(skb_engine *e) {
   CK(cudaEventSynchronize(e->ev_h2d));
   return SKB_OK;
+}
+
+/* Can the stage pipeline of k_render_levels render this voice (the parameter-only part of lane_needs_generic with
+ * levelled = true, free_kernel.cuh)?  What it cannot — S&H, quantize, noise, reverse, smoother off, odd loop windows —
+ * keeps the voice's whole component in the frame-lock-step bins. */
+static bool levelable_voice(const skb_engine *e, int v) {
+  const skb_voice_params &p = e->par[v];
+  if ((p.flags & (SKB_F_NOISE | SKB_F_REVERSE)) || !(p.flags & SKB_F_SMOOTHER) || p.sample_hold_max != 0 || p.quantize != 0) return false;
+  if (p.table_id < 0 || p.table_id >= (int)e->tables.size() || p.table_size <= 0 || p.table_size > 8388608) return false;
+  if (p.cz_mode < 0 || p.cz_mode > 7) return false;
+  const bool use_loop = (p.flags & SKB_F_LOOP_ENABLED) && (p.flags & SKB_F_LOOP_VALID);
+  const float lo = use_loop ? p.loop_start_f : 0.0f, hi = use_loop ? p.loop_end_f : (float)p.table_size;
+  if (!(lo >= 0.0f) || !(hi <= (float)p.table_size) || !(hi > lo)) return false;
+  int live[4];
+  skb_live_mods(&p, v, e->n, live);
+  const bool fm = live[0] >= 0;
+  if (!fm && (!(lo == 0.0f) || !(p.phase_inc >= 0.0f && p.phase_inc < hi))) return false;
+  /* self-references read the voice's own value of this or the last frame: lock-step */
+  if (p.cz_mode != 0 && p.cz_mod_osc == v && p.cz_mod_depth != 0.0f) return false;
+  if (p.amp_mod_osc == v || (p.pan_mod_osc == v && !(p.flags & SKB_F_DISCONNECT))) return false;
+  if (p.cz_mode != 0 && live[1] < 0 && (p.table_size & (p.table_size - 1)) != 0) return false;   /* (untraced CZ needs a 2^k table) */
+  return true;
 }
 
 static int replan(skb_engine *e, cudaStream_t st) {
@@ -579,11 +619,83 @@ static int replan(skb_engine *e, cudaStream_t st) {
       if (e->owner[v] == rank && csize[e->comp[v]] > 1) members[ridx[e->comp[v]]].push_back(v);
   }
   e->bins.clear();
+  /* LEVELS (level_kernel.cuh).  A component whose live edges form a DAG, all of whose voices the stage pipeline can
+   * render, is not stepped frame by frame: its voices are rendered level by level (a voice after every voice it reads),
+   * each level by one launch of k_render_levels, the modulators' samples handed on as per-frame traces.  No size limit. */
+  std::fill(e->lev_of.begin(), e->lev_of.end(), -1);
+  std::fill(e->trace_of.begin(), e->trace_of.end(), -1);
+  for (int v = 0; v < n; v++) e->lev_deps[v].clear();
+  std::vector<int32_t> lev_voices;
+  int max_level = -1;
+  const bool levels_on = !e->tap_on && !(e->cfg.flags & SKB_CFG_FORCE_GENERIC) && !(getenv("SKB_LEVELS") && atoi(getenv("SKB_LEVELS")) == 0);
+  for (size_t i = 0; i < roots.size() && levels_on; i++) {
+    const std::vector<int32_t> &mem = members[i];
+    bool ok = true;
+    for (size_t k = 0; k < mem.size() && ok; k++) ok = levelable_voice(e, mem[k]);
+    if (!ok) continue;
+    /* longest-path levels by relaxation (Kahn): indegree = live modulators inside the component */
+    std::vector<int> indeg(mem.size(), 0), lvl(mem.size(), 0);
+    std::vector<int32_t> local(n > 0 ? 0 : 0);
+    std::vector<std::vector<int>> outs(mem.size());
+    auto idx_of = [&mem](int v) { return (int)(std::lower_bound(mem.begin(), mem.end(), v) - mem.begin()); };
+    for (size_t k = 0; k < mem.size(); k++) {
+      int live[4];
+      skb_live_mods(&e->par[mem[k]], mem[k], n, live);
+      for (int q = 0; q < 4; q++) {
+        if (live[q] < 0 || live[q] == mem[k]) continue;
+        bool dup = false;
+        for (int r = 0; r < q; r++) dup = dup || live[r] == live[q];
+        if (dup) continue;
+        outs[idx_of(live[q])].push_back((int)k);
+        indeg[k]++;
+      }
+    }
+    std::vector<int> queue;
+    for (size_t k = 0; k < mem.size(); k++) if (indeg[k] == 0) queue.push_back((int)k);
+    size_t done = 0;
+    while (done < queue.size()) {
+      const int k = queue[done++];
+      for (size_t j = 0; j < outs[k].size(); j++) {
+        const int d = outs[k][j];
+        lvl[d] = std::max(lvl[d], lvl[k] + 1);
+        if (--indeg[d] == 0) queue.push_back(d);
+      }
+    }
+    if (done != mem.size()) continue;                       /* a cycle: lock-step bins */
+    for (size_t k = 0; k < mem.size(); k++) {
+      e->lev_of[mem[k]] = lvl[k];
+      max_level = std::max(max_level, lvl[k]);
+      lev_voices.push_back(mem[k]);
+      for (size_t j = 0; j < outs[k].size(); j++) e->lev_deps[mem[k]].push_back(mem[outs[k][j]]);
+    }
+    members[i].clear();                                     /* not a bin */
+  }
+  /* slots of the levelled voices: after the free range, level by level (rows never mix levels), voices in index order */
+  e->lev_rows.assign((size_t)(max_level + 1), std::make_pair(0, 0));
+  e->n_traces = 0;
+  {
+    std::stable_sort(lev_voices.begin(), lev_voices.end(), [e](int32_t a2, int32_t b2) {
+      return e->lev_of[a2] != e->lev_of[b2] ? e->lev_of[a2] < e->lev_of[b2] : a2 < b2; });
+    int sl = e->n_free_pad;
+    for (size_t i = 0; i < lev_voices.size(); i++) {
+      const int v = lev_voices[i];
+      if (i > 0 && e->lev_of[v] != e->lev_of[lev_voices[i - 1]]) sl = (sl + 31) & ~31;
+      if (i == 0 || e->lev_of[v] != e->lev_of[lev_voices[i - 1]]) e->lev_rows[e->lev_of[v]].first = sl / 32;
+      e->slot_of_voice[v] = sl;
+      e->voice_of_slot[sl] = v;
+      if (!e->lev_deps[v].empty()) e->trace_of[v] = e->n_traces++;
+      sl++;
+      e->lev_rows[e->lev_of[v]].second = (sl + 31) / 32 - e->lev_rows[e->lev_of[v]].first;
+    }
+    e->n_lev_pad = (sl + 31) & ~31;
+    e->n_lev_rows = (e->n_lev_pad - e->n_free_pad) / 32;
+  }
   /* components of <= 32 voices are packed into bins of <= 32 and rendered one WARP per bin (k_render_bins_warp, batched
    * launches with in-kernel boundary ops); a larger component gets a CTA of its own (k_render_bins) */
   std::vector<std::vector<int32_t>> binv, binv_big;
   for (size_t i = 0; i < roots.size(); i++) {
     const int sz = (int)members[i].size();
+    if (sz == 0) continue;                                  /* levelled */
     if (sz > SKB_BIN_MAX)
       return fail(e, SKB_ERR_CAPACITY, "a modulation group has more than 1024 voices");
     if (sz > SKB_BIN_WARP) { binv_big.push_back(members[i]); continue; }
@@ -592,7 +704,7 @@ static int replan(skb_engine *e, cudaStream_t st) {
   }
   e->n_small_bins = (int)binv.size();
   binv.insert(binv.end(), binv_big.begin(), binv_big.end());
-  int slot = e->n_free_pad;
+  int slot = e->n_lev_pad;
   e->n_free_rows = e->n_free_pad / 32;
   /* partial-row groups: one per (CTA, batch) of k_render_free, then the bins 16 to a group */
   std::vector<int> ctarows;
@@ -774,6 +886,10 @@ static int replan(skb_engine *e, cudaStream_t st) {
         CK(cudaMemcpyAsync(e->d_lists, lists.data(), lists.size() * sizeof(int), cudaMemcpyHostToDevice, st));
       }
       CK(cudaStreamSynchronize(st));          /* pageable sources */
+      if (e->n_traces > 0) {
+        rr = grow_dev(&e->d_trace, &e->trace_cap, (size_t)e->n_traces * (e->cfg.max_frames + 1));
+        if (rr != cudaSuccess) return fail(e, SKB_ERR_CUDA, "modulator trace alloc", cudaGetErrorString(rr));
+      }
       if (e->n_wide_rows > 0) {
         rr = grow_dev(&e->d_snap, &e->snap_cap, (size_t)SKB_NSQ * e->snap_nwin * e->cap);
         if (rr != cudaSuccess) return fail(e, SKB_ERR_CUDA, "window snapshot alloc", cudaGetErrorString(rr));
@@ -784,7 +900,7 @@ static int replan(skb_engine *e, cudaStream_t st) {
       }
     }
   }
-  e->n_prows = e->free_groups + (int)binv.size();
+  e->n_prows = e->free_groups + (int)binv.size() + e->n_lev_rows;      /* (CTA, batch) rows, bins, levelled rows */
   e->max_bin_threads = 0;
   for (size_t b = 0; b < binv.size(); b++) {
     std::sort(binv[b].begin(), binv[b].end());
@@ -896,7 +1012,20 @@ static int sync_inputs(skb_engine *e, cudaStream_t st, bool defer_ops = false) {
     for (size_t i = 0; i < e->dirty_list.size(); i++) {
       const int v = e->dirty_list[i];
       if (edge_signature(&e->par[v], v, e->n) != e->edge_sig[v]) { e->need_plan = true; break; }
+      if (e->lev_of[v] >= 0 && !levelable_voice(e, v)) { e->need_plan = true; break; }   /* e.g. `h` / `q` / `b` on a levelled voice */
     }
+  if (!e->need_plan) {
+    /* the readers of a changed modulator carry its phase increment in their own records */
+    const size_t nd = e->dirty_list.size();
+    for (size_t i = 0; i < nd; i++) {
+      const int v = e->dirty_list[i];
+      if (e->lev_of[v] < 0) continue;
+      for (size_t k = 0; k < e->lev_deps[v].size(); k++) {
+        const int d = e->lev_deps[v][k];
+        if (!e->dirty[d]) { e->dirty[d] = 1; e->dirty_list.push_back(d); }
+      }
+    }
+  }
   if (e->need_plan && replan(e, st)) return e->err;
   cudaError_t r;
   if (!e->dirty_list.empty()) {
@@ -1120,9 +1249,13 @@ static int batch_launch(skb_engine *e) {
   const std::vector<int> &cta_of = wide ? e->cta_of_row_wide : e->cta_of_row;
   const int ncta = rows ? e->n_free_rows : std::max(e->free_ctas, 1);
   const int n_free_pad = e->n_free_pad;
-  const int nbk = ncta + 1;                                  /* op buckets: the CTAs (rows) of the free kernel, then the bins */
-  auto cta_of_slot = [&cta_of, n_free_pad, rows, ncta](int slot) {
-    return (slot >= 0 && slot < n_free_pad) ? (rows ? (slot >> 5) : cta_of[(size_t)(slot >> 5)]) : ncta; };
+  /* op buckets: the CTAs (rows) of the free kernel, then the bins (one bucket), then the levelled rows (one each) */
+  const int nbk = ncta + 1 + e->n_lev_rows;
+  const int n_lev_pad = e->n_lev_pad;
+  auto cta_of_slot = [&cta_of, n_free_pad, n_lev_pad, rows, ncta](int slot) {
+    if (slot >= 0 && slot < n_free_pad) return rows ? (slot >> 5) : cta_of[(size_t)(slot >> 5)];
+    if (slot >= n_free_pad && slot < n_lev_pad) return ncta + 1 + ((slot - n_free_pad) >> 5);
+    return ncta; };
   for (size_t i = 0; i < nops; i++) e->batch.ops[i]._pad = cta_of_slot(e->batch.ops[i].voice);   /* bucket key; the kernel ignores it */
   cudaError_t r;
   if (wait_staging(e)) return e->err;
@@ -1280,6 +1413,28 @@ static int batch_launch(skb_engine *e) {
                                                          e->tap_on ? e->n : 0);
     e->stats.kernel_launches++;
   }
+  if (e->n_lev_rows > 0) {
+    /* one launch per level, in level order: a level reads the traces the levels before it wrote */
+    FreeArgs fl;
+    memset(&fl, 0, sizeof(fl));
+    fl.pq = e->d_pq; fl.sq = e->d_sq[e->cur]; fl.cap = e->cap; fl.n_rows = e->n_lev_rows; fl.n_free = e->n_lev_pad;
+    fl.tables = e->d_tables; fl.noise = e->d_noise;
+    fl.nframes = nframes; fl.ssc_before = (unsigned long long)e->batch.ssc0;
+    fl.win_frames = d_winp; fl.win_ob = d_winp + nwin; fl.nwin = nwin; fl.ob_stride = nbk + 1;
+    fl.bops = d_bopsp; fl.wake = d_wake;
+    fl.ctarows = e->d_partials; fl.row_stride = nframes;
+    fl.counters = e->d_counters; fl.force_generic = 0;
+    fl.trace = e->d_trace; fl.trace_stride = e->cfg.max_frames + 1;
+    const int first_row = e->n_free_pad / 32;
+    for (size_t L = 0; L < e->lev_rows.size(); L++) {
+      if (e->lev_rows[L].second <= 0) continue;
+      fl.row0 = e->lev_rows[L].first;
+      fl.group0 = e->free_groups + (int)e->bins.size() + (fl.row0 - first_row);
+      fl.ob_bucket0 = ncta + 1 + (fl.row0 - first_row);
+      k_render_levels<<<e->lev_rows[L].second, RP_THREADS, skb_levels_smem_bytes(), st>>>(fl);
+      e->stats.kernel_launches++;
+    }
+  }
   if (n_prows_now > 0) {
     dim3 blk(SKB_RED_X, SKB_RED_Y);
     dim3 grd((nframes + SKB_RED_X - 1) / SKB_RED_X, std::max(1, std::min(SKB_RED_CHUNKS, n_prows_now / 16)));
@@ -1324,6 +1479,10 @@ int skb_render_mix(skb_engine *e, int nframes, uint64_t ssc_before, const float 
                 e->batch.frames + nframes <= e->cfg.max_frames && bins_batch_ok(e) && e->planned && !e->need_plan &&
                 e->dirty_list.empty() && !(e->cfg.flags & SKB_CFG_NO_BATCH);
   if (extend && !e->ops.empty() && e->batch.frames % SKB_ENV_WIN != 0) extend = false;   /* (boundaries are window starts) */
+  if (extend && e->n_lev_rows > 0)
+    /* voice_reset clears voice_sample between two callbacks: a modulator's trace cannot say "0 from here on, but the old
+     * value for the frame before" — such a boundary starts a new launch (trace[0] then holds the cleared value) */
+    for (size_t i = 0; i < e->ops.size() && extend; i++) if (e->ops[i].code == SKB_OP_VOICE_CLEAR) extend = false;
   if (!extend) {
     if (batch_launch(e)) return e->err;
     if (use_stream(e, st)) return e->err;
@@ -1453,6 +1612,7 @@ int skb_set_tap(skb_engine *e, int enable) {
     cudaError_t r = grow_dev(&e->d_tap, &e->tap_cap, need);
     if (r != cudaSuccess) return fail(e, SKB_ERR_CUDA, "tap alloc", cudaGetErrorString(r));
   }
+  if (e->tap_on != (enable != 0)) e->need_plan = true;     /* (levelled voices have no tap: with the tap on they go to the bins) */
   e->tap_on = enable != 0;
   e->tap_cursor = 0;
   return e->err;

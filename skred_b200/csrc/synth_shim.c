@@ -163,6 +163,24 @@ static void push_op(int v, int code, int i0, float f0, float f1, uint64_t u0) {
   o->voice = v; o->code = code; o->i0 = i0; o->f0 = f0; o->f1 = f1; o->_pad = 0; o->u0 = u0;
 }
 
+/* Fingerprint of a user wave slot: 64 samples spread over the table (their bit patterns, position-mixed).  wire.c edits a
+ * loaded sample IN PLACE (`/wex` -> wave_table_dynamic_expand, wire.c:553-586, scales every sample; same pointer, same
+ * size) without telling synth.c; the device copy is refreshed when the fingerprint of a slot in use has changed. */
+static uint64_t g_slot_fp[WAVE_TABLE_MAX];
+static uint64_t slot_fingerprint(int wave) {
+  const float *d = wave_table_data[wave];
+  const int n = wave_size[wave];
+  uint64_t h = 1469598103934665603ull;
+  if (!d || n <= 0) return h;
+  for (int k = 0; k < 64; k++) {
+    const int i = (int)(((long long)k * (n - 1)) / 63);
+    uint32_t b;
+    memcpy(&b, &d[i], 4);
+    h = (h ^ (uint64_t)b ^ ((uint64_t)i << 32)) * 1099511628211ull;
+  }
+  return h;
+}
+
 static int32_t slot_table_id(int wave) {
   engine();
   if (g_slot_tid[wave] >= 0 && g_slot_ptr[wave] == wave_table_data[wave] &&
@@ -173,7 +191,22 @@ static int32_t slot_table_id(int wave) {
   g_slot_ptr[wave] = wave_table_data[wave];
   g_slot_size[wave] = wave_size[wave];
   g_slot_tid[wave] = tid;
+  g_slot_fp[wave] = slot_fingerprint(wave);
   return tid;
+}
+
+/* Called at every block boundary: a user slot (EXT_SAMPLE_000 ... 999) whose data changed under the same pointer is
+ * uploaded again and every voice that plays it is re-pointed — the reference reads the edited floats from the next
+ * frame on (its table IS the edited array).  ~800 compares per call when nothing is loaded. */
+static void refresh_edited_tables(void) {
+  for (int wave = EXT_SAMPLE_000; wave < WAVE_TABLE_MAX; wave++) {
+    if (g_slot_tid[wave] < 0 || g_slot_ptr[wave] != wave_table_data[wave] || g_slot_size[wave] != wave_size[wave]) continue;
+    if (slot_fingerprint(wave) == g_slot_fp[wave]) continue;
+    g_slot_tid[wave] = -1;
+    const int32_t tid = slot_table_id(wave);
+    for (int v = 0; v < VOICE_MAX; v++)
+      if (voice_table[v] == wave_table_data[wave] && voice_wave_table_index[v] == wave) { g_voice_tid[v] = tid; touch(v); }
+  }
 }
 
 /* Force a re-upload of a slot whose contents were edited in place
@@ -236,6 +269,7 @@ static void send_if_changed(int v) {
  * since the previous block becomes visible to the device here. */
 int skb_shim_flush(void) {
   engine();
+  refresh_edited_tables();
   if (g_scan_all) {
     for (int v = 0; v < VOICE_MAX; v++) send_if_changed(v);
     for (int i = 0; i < g_ndirty; i++) g_dirty[g_dirty_list[i]] = 0;

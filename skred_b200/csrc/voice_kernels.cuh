@@ -23,12 +23,13 @@
 #include <math_constants.h>
 #include "skred_b200.h"
 
-#define SKB_NPQ 8          /* float4 groups per voice: parameters (32 words) */
+#define SKB_NPQ 9          /* float4 groups per voice: parameters (32 words + the words of a levelled modulated voice) */
 #define SKB_NSQ 5          /* float4 groups per voice: evolving state (18 of 20 words) */
 #define SKB_REF_NONE (-1)      /* no modulator: the reference's literal for that site (1.0f / no FM) */
 #define SKB_REF_SELF (-2)      /* the voice reads its own voice_sample */
 #define SKB_REF_ZERO (-3)      /* modulator contributes an identical 0.0f (depth-0 CZ default, out-of-range osc) */
 #define SKB_REF_CUR  (1 << 20)   /* read the modulator's CURRENT-frame value (m < n) */
+#define SKB_REF_TRACE (1 << 21)  /* the modulator is rendered by an EARLIER launch: read its per-frame trace (row = ref & MASK) */
 #define SKB_REF_MASK ((1 << 20) - 1)
 
 struct VoiceP {
@@ -40,6 +41,8 @@ struct VoiceP {
   float a2, envA, envD, envS;
   float envR, am_depth, sm_k, pm_depth;
   int fmode, am_ref, pm_ref, level;
+  float fm_minc;             /* levelled voice: voice_phase_inc of its FM modulator (synth.c:553: inc[mod]) */
+  int trace_out;             /* levelled voice: trace row its voice_sample goes to (somebody reads it), or -1 */
 };
 
 struct VoiceS {
@@ -67,6 +70,7 @@ __device__ __forceinline__ void load_params(const float4 *__restrict__ q, int ca
   a = ldq(q, 5, cap, slot); p.a2 = a.x; p.envA = a.y; p.envD = a.z; p.envS = a.w;
   a = ldq(q, 6, cap, slot); p.envR = a.x; p.am_depth = a.y; p.sm_k = a.z; p.pm_depth = a.w;
   a = ldq(q, 7, cap, slot); p.fmode = __float_as_int(a.x); p.am_ref = __float_as_int(a.y); p.pm_ref = __float_as_int(a.z); p.level = __float_as_int(a.w);
+  a = ldq(q, 8, cap, slot); p.fm_minc = a.x; p.trace_out = __float_as_int(a.y) - 1;      /* (stored + 1: a cleared record reads "none") */
 }
 
 __device__ __forceinline__ void load_state(const float4 *__restrict__ q, int cap, int slot, VoiceS &s) {
@@ -212,6 +216,17 @@ struct NoMods {
   __device__ __forceinline__ float inc_of(int) const { return 0.0f; }
 };
 
+/* Modulators of a LEVELLED voice: every voice it reads was rendered by an earlier launch of the same step and left its
+ * voice_sample of every frame in a trace row: trace[row][0] = the value before the launch, [1 + f] = after frame f.  A
+ * modulator with a smaller voice index is read at the current frame, a larger one at the previous frame (synth.c:526). */
+struct TraceMods {
+  const float *trace; int stride; int frame; float minc;
+  __device__ __forceinline__ float read(int ref) const {
+    return trace[(size_t)(ref & SKB_REF_MASK) * stride + frame + ((ref & SKB_REF_CUR) ? 1 : 0)];
+  }
+  __device__ __forceinline__ float inc_of(int) const { return minc; }
+};
+
 template <bool MODS, class Mod>
 __device__ __forceinline__ float mod_value(int ref, float self_value, const Mod &mod) {
   if (ref == SKB_REF_SELF) return self_value;
@@ -327,6 +342,7 @@ __device__ __forceinline__ void dev_apply_op(VoiceS &s, const skb_op &op) {
 /* K1  render_free: free_kernel.cuh; K1b render_rows (few voices per GPU): row_kernel.cuh */
 #include "free_kernel.cuh"
 #include "row_kernel.cuh"
+#include "level_kernel.cuh"
 
 /* ======================================================================== */
 /* K2  render_bins: modulation groups, frame-lock-step                       */

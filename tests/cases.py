@@ -141,3 +141,23 @@ def drive_setup(s, wl):
 
 def drive_render(s, wl, frames=None):
     return s.render(wl["frames"] if frames is None else frames, events=wl["events"])
+
+
+def wex_scenario(s):
+    """`/wex<slot>` (wave_table_dynamic_expand, wire.c:553-586) rescales a loaded user sample IN PLACE — same pointer, same
+    size — while voices play it; the reference reads the edited floats from the next frame on.  A user table with peaks
+    beyond +-1 in slot 300, six voices on it (plain, CZ, filtered), two callbacks, `/wex300`, three more callbacks.
+    Returns (mix, state)."""
+    from skred_b200.host import install_table
+    rng = np.random.RandomState(11)
+    tbl = (2.5 * np.sin(np.linspace(0, 6 * np.pi, 1024)) + 0.3 * rng.randn(1024)).astype(np.float32)
+    install_table(s, 300, tbl)
+    s._wex_table = tbl                        # (the library reads this memory: keep it alive)
+    for v in range(6):
+        s.wire("v%d w300 f%d a0.1 p%.1f" % (v, 110 * (v + 1), (v - 3) / 4.0))
+    s.wire("v2 c1,0.4")
+    s.wire("v3 J1 K900 Q2")
+    out = [s.render(1024)]
+    s.wire("/wex300")
+    out.append(s.render(1536))
+    return np.concatenate(out), s.state()

@@ -430,3 +430,15 @@ def test_sharded_render_n_gpus_vs_reference(world, tmp_path):
     assert r.returncode == 0, r.stdout[-3000:]
     txt = open(out).read()
     assert txt.count("-> OK") == 2 and "FAIL" not in txt, txt
+
+
+def test_wex_in_place_table_edit_vs_reference():
+    """`/wex<slot>` (wave_table_dynamic_expand, wire.c:553-586) rescales a loaded user sample in place while voices play
+    it; the CUDA drop-in re-uploads the slot when its fingerprint changes (no host cooperation needed).  Against the
+    compiled reference: mix <= 1e-5, every evolving word bit for bit."""
+    if not O.have_ref(64):
+        pytest.skip("compiled reference not present")
+    a, sa = cases.wex_scenario(O.RefSkred(64))
+    b, sb = cases.wex_scenario(O.DropinCuda(64))
+    assert maxdiff(a, b) <= FULL_SCALE_TOL
+    assert_state_equal(sa, sb, exact_keys=EXACT)

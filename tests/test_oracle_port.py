@@ -1,6 +1,8 @@
 """CPU: pin the oracle.  The restatement (oracle/skred_port.c behind the product's
 host shim) must equal the compiled reference (oracle/_ref) BIT FOR BIT, and both
 must equal the committed golden fixtures generated from the reference."""
+import os
+
 import numpy as np
 import pytest
 
@@ -161,3 +163,18 @@ def test_every_shipped_patch_shim_over_port_equals_reference():
         assert mix and state is True, (n, mix, state)
         sounding += peak > 0.0
     assert sounding >= 40
+
+
+def test_wex_in_place_table_edit_port_vs_reference():
+    """`/wex` edits a user sample in place (wire.c:553-586); the drop-in notices the changed floats at the next block
+    boundary (synth_shim.c: refresh_edited_tables) and uploads the table again.  Shim over the CPU restatement vs the
+    compiled reference: mix and every evolving word equal."""
+    import cases
+    from tests_util import assert_state_equal, FULL_SCALE_TOL
+    if not (O.have_ref(64) and os.path.exists(O.port_lib_path(64))):
+        pytest.skip("oracle libraries not built")
+    a, sa = cases.wex_scenario(O.RefSkred(64))
+    b, sb = cases.wex_scenario(O.PortSkred(64))
+    assert float(np.max(np.abs(a.astype(np.float64) - b))) <= FULL_SCALE_TOL
+    assert float(np.abs(a[1024:]).max()) > 1e-4 and not np.allclose(a[:1024], a[1024:2048])
+    assert_state_equal(sa, sb)
