@@ -231,6 +231,14 @@ float *skb_mix_buffer(skb_engine *e);
  * 65,536 voices), so it is off until asked for; time-split launches are not used while it is on. */
 int  skb_set_tap(skb_engine *e, int enable);
 int  skb_read_tap(skb_engine *e, int frame0, int nframes, float *out);
+/* Selective read-back (skred.c:120-131 and wire.c:94-185 only ever WRITE the voices with voice_record[v] set,
+ * wire.c:698).  skb_set_tap_voices names the voices whose tap the host wants (n = 0: every voice); skb_read_tap_selected
+ * copies only their columns, out[nframes][n_selected][2] in the order given, over PCIe — 8 bytes per SELECTED
+ * voice-sample instead of 8 bytes per voice-sample — and reports in extremes[2] = {min(0, x), max(0, x)} over the samples
+ * of the voices NOT selected: save_wav scales by the extremes of all voices of the recording (wire.c:150-166), so a host
+ * that wants the reference's file bit for bit needs those two numbers and nothing else of the unselected voices. */
+int  skb_set_tap_voices(skb_engine *e, const int32_t *voices, int n);
+int  skb_read_tap_selected(skb_engine *e, int frame0, int nframes, float *out, float *extremes);
 /* Wait for everything queued on `stream` (NULL = engine stream). */
 int  skb_sync(skb_engine *e, void *stream);
 

@@ -106,6 +106,12 @@ void skb_shim_discard_gain(void);
  * (skb_shim_render_mix x ncalls + skb_shim_flush_render). */
 int skb_shim_render_calls(int frames_per_call, int ncalls, float *d_mix, void *stream);
 
+/* Per-voice tap `user` of synth(): read back only the voices being recorded (voice_record[], wire.c:698) instead of every
+ * voice (8 bytes per voice-sample over PCIe).  The other voices' entries stay 0, except one carrier pair per call that
+ * holds the extremes save_wav's scale depends on, so the written WAV equals the reference's (synth_shim.c, tests).
+ * Also switched on by SKB_TAP_SELECTIVE=1.  Call before the first synth(). */
+void skb_shim_tap_selective(int on);
+
 /* Diagnostics: host-side seconds spent inside synth() since the last reset: [0] flush + master-volume / noise
  * trace stepping, [1] skb_render_mix (queueing the segments), [2] firing due events (setters -> device ops),
  * [3] skb_finish (launch, kernels, D2H, synchronisation) and the tap readback. */

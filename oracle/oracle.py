@@ -101,6 +101,23 @@ class HarnessSkred(SynthAPI):
             k += 1
         return out, taps
 
+    def record_init(self, max_sec=1.0, block=BLOCK):
+        """skred.c's synth_callback_init + the per-voice tap: call before the first render."""
+        self.lib.ref_record_init.argtypes = [C.c_float, C.c_int]
+        self.lib.ref_enable_tap.restype = C.c_void_p
+        self.lib.ref_enable_tap.argtypes = [C.c_int]
+        self.lib.ref_record_init(max_sec, block)
+        self.lib.ref_render_recording.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int]
+        self.lib.ref_render_recording.restype = C.c_double
+        self.lib.ref_rec_ptr.restype = C.c_long
+
+    def render_recording(self, nframes, block=BLOCK):
+        """render() through the body of synth_callback (skred.c:116-131): while `<sec` is recording, every callback's
+        per-voice tap is appended to the recording buffer that `*` writes out with save_wav (wire.c:94-185)."""
+        out = np.zeros((nframes, 2), dtype=np.float32)
+        self.lib.ref_render_recording(out.ctypes.data, nframes, block, self.run_seq)
+        return out
+
     def engine_stats(self):
         """skb_stats of the engine behind a drop-in build (port: linked in; cuda: libskred_b200.so)."""
         from skred_b200.host import skb_stats

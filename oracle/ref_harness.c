@@ -190,6 +190,43 @@ double ref_render(float *out, long nframes, int block, int run_seq) {
 
 uint64_t ref_sample_count(void) { return synth_sample_count; }
 
+/* ---- recording (skred.c:84-131, wire.c `<sec` / `*`): what synth_callback does with the per-voice tap ---- */
+/* synth_callback_init(max_sec), skred.c:93-100, with a test-sized buffer; call before the first ref_render*.
+ * The tap is sized for callbacks of `block` frames (synth() latches it on its first call). */
+void ref_record_init(float max_sec, int block) {
+  free(recording);
+  rec_sec = max_sec;
+  rec_max = (long)(max_sec * (float)(MAIN_SAMPLE_RATE * AUDIO_CHANNELS * VOICE_MAX));
+  recording = (float *)malloc((size_t)rec_max * sizeof(float));
+  if (!g_tap || g_tap_frames < block) ref_enable_tap(block);
+}
+
+/* ref_render with the body of synth_callback (skred.c:116-131): synth(); seq(); then, while rec_state is set, the tap of
+ * EVERY voice of the callback is appended to the recording. */
+double ref_render_recording(float *out, long nframes, int block, int run_seq) {
+  long done = 0;
+  while (done < nframes) {
+    int n = (nframes - done) < block ? (int)(nframes - done) : block;
+    synth(out + done * 2, NULL, n, 2, g_tap);
+    if (run_seq) seq(n);
+    if (rec_state) {
+      float *f = g_tap;
+      for (long i = 0; i < (long)n * 2 * VOICE_MAX; i += 2) {
+        if (rec_ptr < rec_max) {
+          recording[rec_ptr++] = f[i];
+          recording[rec_ptr++] = f[i + 1];
+        } else {
+          rec_state = 0;
+          break;
+        }
+      }
+    }
+    done += n;
+  }
+  return 0.0;
+}
+long ref_rec_ptr(void) { return rec_ptr; }
+
 /* Install a caller-owned float table into a wave slot the way data_load does
  * (wire.c:374-404) but with explicit loop/one-shot fields, so the dead
  * notamy LUTs can be exercised.  The table is copied. */

@@ -47,6 +47,8 @@ struct skb_engine {
   float *mix;           /* scratch for skb_render */
   float *tap;           /* per-voice tap [max_frames][n][2] (synth.c:533-611), NULL = off */
   int tap_cursor;       /* frames rendered since the last skb_finish */
+  int32_t *tap_sel;     /* voices whose tap is read back by skb_read_tap_selected (n_tap_sel = 0: all) */
+  int n_tap_sel;
   int err;
   char errtxt[256];
   skb_stats stats;
@@ -84,7 +86,7 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
 void skb_destroy(skb_engine *e) {
   if (!e) return;
   for (int i = 0; i < e->n_tables; i++) free(e->tables[i].data);
-  free(e->tables); free(e->par); free(e->st); free(e->owner); free(e->ops); free(e->mix); free(e->tap);
+  free(e->tables); free(e->par); free(e->st); free(e->owner); free(e->ops); free(e->mix); free(e->tap); free(e->tap_sel);
   free(e);
 }
 
@@ -408,6 +410,41 @@ int skb_set_tap(skb_engine *e, int enable) {
 int skb_read_tap(skb_engine *e, int frame0, int nframes, float *out) {
   if (!e || !out || !e->tap || frame0 < 0 || nframes < 0 || frame0 + nframes > e->cfg.max_frames) return SKB_ERR_ARG;
   memcpy(out, e->tap + (size_t)frame0 * e->n * 2, (size_t)nframes * e->n * 2 * sizeof(float));
+  return e->err;
+}
+
+int skb_set_tap_voices(skb_engine *e, const int32_t *voices, int n) {
+  if (!e || n < 0 || (n > 0 && !voices)) return SKB_ERR_ARG;
+  free(e->tap_sel);
+  e->tap_sel = n ? (int32_t *)malloc((size_t)n * sizeof(int32_t)) : NULL;
+  if (n) memcpy(e->tap_sel, voices, (size_t)n * sizeof(int32_t));
+  e->n_tap_sel = n;
+  return e->err;
+}
+
+/* the selected columns, and min(0, x) / max(0, x) over the samples of every other voice (what save_wav's scale needs
+ * of them, wire.c:150-166) */
+int skb_read_tap_selected(skb_engine *e, int frame0, int nframes, float *out, float *extremes) {
+  if (!e || !out || !e->tap || frame0 < 0 || nframes < 0 || frame0 + nframes > e->cfg.max_frames) return SKB_ERR_ARG;
+  if (extremes) extremes[0] = extremes[1] = 0.0f;
+  if (e->n_tap_sel == 0) return skb_read_tap(e, frame0, nframes, out);
+  int *col = (int *)malloc((size_t)e->n * sizeof(int));
+  for (int v = 0; v < e->n; v++) col[v] = -1;
+  for (int i = 0; i < e->n_tap_sel; i++) col[e->tap_sel[i]] = i;
+  float small = 0.0f, big = 0.0f;
+  for (int f = 0; f < nframes; f++) {
+    const float *src = e->tap + (size_t)(frame0 + f) * e->n * 2;
+    for (int v = 0; v < e->n; v++) {
+      if (col[v] >= 0) {
+        out[((size_t)f * e->n_tap_sel + col[v]) * 2 + 0] = src[2 * v];
+        out[((size_t)f * e->n_tap_sel + col[v]) * 2 + 1] = src[2 * v + 1];
+      } else {
+        for (int k = 0; k < 2; k++) { const float g = src[2 * v + k]; if (g > big) big = g; if (g < small) small = g; }
+      }
+    }
+  }
+  free(col);
+  if (extremes) { extremes[0] = small; extremes[1] = big; }
   return e->err;
 }
 

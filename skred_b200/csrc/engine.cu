@@ -95,6 +95,11 @@ struct skb_engine {
   float2 *d_tap = nullptr; size_t tap_cap = 0;      /* [max_frames][n] */
   int *d_vos = nullptr; size_t vos_cap = 0;          /* voice of slot */
   float2 *h_tap = nullptr; size_t h_tap_cap = 0;
+  std::vector<int32_t> tap_sel;                     /* voices whose tap is read back (empty = all) */
+  int *d_tapcol = nullptr; size_t tapcol_cap = 0;    /* per voice: column in the compact copy, -1 = not selected */
+  float2 *d_tapsel = nullptr; size_t tapsel_cap = 0; /* compact copy [frames][selected] */
+  unsigned int *d_tapext = nullptr;                  /* extremes of the voices not selected (bit patterns) */
+  bool tapcol_dirty = true;
 
   /* device */
   float4 *d_pq = nullptr, *d_sq[2] = {nullptr, nullptr};
@@ -367,6 +372,7 @@ void skb_destroy(skb_engine *e) {
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   cudaFree(e->d_lists); cudaFree(e->d_xrow); cudaFree(e->d_snap); cudaFree(e->d_xs);
   cudaFree(e->d_tap); cudaFree(e->d_vos); cudaFreeHost(e->h_tap);
+  cudaFree(e->d_tapcol); cudaFree(e->d_tapsel); cudaFree(e->d_tapext);
   if (e->ev_a) cudaEventDestroy(e->ev_a);
   if (e->ev_b) cudaEventDestroy(e->ev_b);
   cudaFree(e->d_part2); cudaFree(e->d_tickets); cudaFree(e->d_counters);
@@ -1629,6 +1635,53 @@ int skb_read_tap(skb_engine *e, int frame0, int nframes, float *out) {
   CK(cudaMemcpyAsync(out, e->d_tap + (size_t)frame0 * e->n, (size_t)nframes * e->n * sizeof(float2), cudaMemcpyDeviceToHost, st));
   e->stats.d2h_bytes += (uint64_t)nframes * e->n * sizeof(float2);
   CK(cudaStreamSynchronize(st));
+  return e->err;
+}
+
+int skb_set_tap_voices(skb_engine *e, const int32_t *voices, int n) {
+  if (!e || n < 0 || (n > 0 && !voices)) return fail(e, SKB_ERR_ARG, "set_tap_voices: bad argument");
+  for (int i = 0; i < n; i++) if (voices[i] < 0 || voices[i] >= e->n) return fail(e, SKB_ERR_ARG, "set_tap_voices: bad voice");
+  e->tap_sel.assign(voices, voices + n);
+  e->tapcol_dirty = true;
+  return e->err;
+}
+
+int skb_read_tap_selected(skb_engine *e, int frame0, int nframes, float *out, float *extremes) {
+  if (!e || !out || frame0 < 0 || nframes < 0 || frame0 + nframes > e->cfg.max_frames) return fail(e, SKB_ERR_ARG, "read_tap_selected: bad argument");
+  if (!e->tap_on || !e->d_tap) return fail(e, SKB_ERR_STATE, "read_tap_selected: the tap is off");
+  if (e->tap_sel.empty()) {                                  /* everything selected: the plain copy, no voice left out */
+    if (extremes) extremes[0] = extremes[1] = 0.0f;
+    return skb_read_tap(e, frame0, nframes, out);
+  }
+  if (nframes == 0) return e->err;
+  cudaSetDevice(e->cfg.device);
+  if (batch_launch(e)) return e->err;
+  cudaStream_t st = e->last_stream ? e->last_stream : e->stream;
+  const int nsel = (int)e->tap_sel.size();
+  cudaError_t r;
+  if (e->tapcol_dirty) {
+    std::vector<int> col((size_t)e->n, -1);
+    for (int i = 0; i < nsel; i++) col[e->tap_sel[i]] = i;
+    if ((r = grow_dev(&e->d_tapcol, &e->tapcol_cap, (size_t)e->n)) != cudaSuccess) return fail(e, SKB_ERR_CUDA, "tap column map alloc", cudaGetErrorString(r));
+    CK(cudaMemcpyAsync(e->d_tapcol, col.data(), (size_t)e->n * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));                           /* pageable source */
+    e->tapcol_dirty = false;
+  }
+  if (!e->d_tapext) CK(cudaMalloc((void **)&e->d_tapext, 2 * sizeof(unsigned int)));
+  const size_t need = (size_t)nframes * nsel;
+  if ((r = grow_dev(&e->d_tapsel, &e->tapsel_cap, need)) != cudaSuccess || (r = grow_pin(&e->h_tap, &e->h_tap_cap, need + 1)) != cudaSuccess)
+    return fail(e, SKB_ERR_CUDA, "tap selection alloc", cudaGetErrorString(r));
+  CK(cudaMemsetAsync(e->d_tapext, 0, 2 * sizeof(unsigned int), st));
+  const size_t items = (size_t)e->n * nframes;
+  k_tap_select<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(e->d_tap + (size_t)frame0 * e->n, e->n, nframes, e->d_tapcol, nsel,
+                                                               e->d_tapsel, e->d_tapext);
+  e->stats.kernel_launches++;
+  CK(cudaMemcpyAsync(e->h_tap, e->d_tapsel, need * sizeof(float2), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(e->h_tap + need, e->d_tapext, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+  e->stats.d2h_bytes += (uint64_t)(need * sizeof(float2) + 8);
+  CK(cudaStreamSynchronize(st));
+  memcpy(out, e->h_tap, need * sizeof(float2));
+  if (extremes) memcpy(extremes, e->h_tap + need, 2 * sizeof(float));
   return e->err;
 }
 

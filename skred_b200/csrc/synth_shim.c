@@ -1107,6 +1107,62 @@ void skb_shim_timing(double *out4, int reset) {
   for (int i = 0; i < 4; i++) { if (out4) out4[i] = g_shim_time[i]; if (reset) g_shim_time[i] = 0.0; }
 }
 
+/* ---- selective per-voice tap ----------------------------------------------------------------------
+ * The reference writes one_skred_frame[frame][voice][L, R] for EVERY voice every frame (synth.c:533-611) although only
+ * the voices with voice_record[v] set are ever written to disk (wire.c:94-185, 698): 8 bytes per voice-sample, all of
+ * it over PCIe here.  With skb_shim_tap_selective(1) (or SKB_TAP_SELECTIVE=1) the device keeps the full tap but only the
+ * columns of the recorded voices come back; the other voices' entries of `user` stay 0 except the FIRST unrecorded
+ * voice of frame 0 of a call, which carries (min(0, x), max(0, x)) over all the samples that did not come back:
+ * save_wav scales by the extremes of every voice of the recording (wire.c:150-166) and skips unrecorded voices when it
+ * writes, so the WAV file is the reference's byte for byte (tests). */
+static int g_tap_selective = -1;                  /* -1 = read SKB_TAP_SELECTIVE on first use */
+static int *g_tap_sel = NULL, g_tap_nsel = 0, g_tap_carrier = -1;
+static unsigned char *g_tap_was = NULL;           /* voice_record[] as of the last call */
+static float *g_tap_compact = NULL; static size_t g_tap_compact_cap = 0;
+static int g_tap_frames_seen = 0;
+void skb_shim_tap_selective(int on) { g_tap_selective = on ? 1 : 0; }
+
+static void tap_sync_selection(float *tap_user) {
+  if (!g_tap_was) { g_tap_was = (unsigned char *)calloc(VOICE_MAX, 1); g_tap_sel = (int *)malloc(sizeof(int) * VOICE_MAX); g_tap_nsel = -1; }
+  int changed = g_tap_nsel < 0;
+  for (int v = 0; v < VOICE_MAX && !changed; v++) changed = (voice_record[v] != 0) != (g_tap_was[v] != 0);
+  if (!changed) return;
+  g_tap_nsel = 0; g_tap_carrier = -1;
+  for (int v = 0; v < VOICE_MAX; v++) {
+    const int on = voice_record[v] != 0;
+    if (on) g_tap_sel[g_tap_nsel++] = v; else if (g_tap_carrier < 0) g_tap_carrier = v;
+    if (!on && g_tap_was[v])                       /* no longer recorded: its column reads 0 again */
+      for (int f = 0; f < g_tap_frames_seen; f++) tap_user[((size_t)f * VOICE_MAX + v) * 2] = tap_user[((size_t)f * VOICE_MAX + v) * 2 + 1] = 0.0f;
+    g_tap_was[v] = (unsigned char)on;
+  }
+  /* an empty selection would mean "all" to the engine: nothing recorded = a selection of one dummy column (the carrier) */
+  if (skb_set_tap_voices(g_engine, g_tap_sel, g_tap_nsel) != SKB_OK) shim_die("skb_set_tap_voices");
+}
+
+static void tap_read_selected(float *tap_user, int chunk0, int frames) {
+  if (g_tap_nsel == VOICE_MAX) {                   /* every voice is recorded: the plain copy */
+    if (skb_read_tap(g_engine, 0, frames, tap_user + (size_t)chunk0 * VOICE_MAX * 2) != SKB_OK) shim_die("skb_read_tap");
+    return;
+  }
+  float ext[2] = {0.0f, 0.0f};
+  if (g_tap_nsel > 0) {
+    const size_t need = (size_t)frames * g_tap_nsel * 2;
+    if (need > g_tap_compact_cap) { g_tap_compact_cap = need * 2; g_tap_compact = (float *)realloc(g_tap_compact, g_tap_compact_cap * sizeof(float)); }
+    if (skb_read_tap_selected(g_engine, 0, frames, g_tap_compact, ext) != SKB_OK) shim_die("skb_read_tap_selected");
+    for (int f = 0; f < frames; f++) {
+      float *dst = tap_user + (size_t)(chunk0 + f) * VOICE_MAX * 2;
+      const float *src = g_tap_compact + (size_t)f * g_tap_nsel * 2;
+      for (int i = 0; i < g_tap_nsel; i++) { dst[2 * g_tap_sel[i]] = src[2 * i]; dst[2 * g_tap_sel[i] + 1] = src[2 * i + 1]; }
+    }
+  }
+  /* nothing selected: nothing is written to disk either (save_wav returns early, wire.c:106-109): no read-back at all */
+  if (g_tap_carrier >= 0 && g_tap_nsel > 0) {
+    float *c = tap_user + ((size_t)chunk0 * VOICE_MAX + g_tap_carrier) * 2;
+    c[0] = ext[0]; c[1] = ext[1];
+  }
+  if (chunk0 + frames > g_tap_frames_seen) g_tap_frames_seen = chunk0 + frames;
+}
+
 void synth(float *buffer, float *input, int num_frames, int num_channels, void *user) {
   (void)input;
   /* `user`: the per-voice tap one_skred_frame[frame][voice][L,R], latched on the FIRST call only like the
@@ -1118,7 +1174,9 @@ void synth(float *buffer, float *input, int num_frames, int num_channels, void *
     tap_user = (float *)user;
     first = 0;
     if (tap_user && skb_set_tap(engine(), 1) != SKB_OK) shim_die("skb_set_tap");
+    if (g_tap_selective < 0) { const char *s = getenv("SKB_TAP_SELECTIVE"); g_tap_selective = (s && atoi(s)) ? 1 : 0; }
   }
+  if (tap_user && g_tap_selective == 1) { engine(); tap_sync_selection(tap_user); }
   const int slot = (int)(g_bench_n % SHIM_BENCH_SLOTS);
   clock_gettime(CLOCK_MONOTONIC, &g_bench[slot].a);
   g_bench[slot].frames = num_frames; g_bench[slot].order = g_bench_n; g_bench[slot].state = 1;
@@ -1169,7 +1227,8 @@ void synth(float *buffer, float *input, int num_frames, int num_channels, void *
     const double t_f = shim_now();
     if (skb_finish(g_engine, d_mix, chunk1 - chunk0, g_gain, buffer + (size_t)chunk0 * num_channels, num_channels, NULL) != SKB_OK)
       shim_die("skb_finish");
-    if (tap_user && skb_read_tap(g_engine, 0, chunk1 - chunk0, tap_user + (size_t)chunk0 * VOICE_MAX * 2) != SKB_OK)
+    if (tap_user && g_tap_selective == 1) tap_read_selected(tap_user, chunk0, chunk1 - chunk0);
+    else if (tap_user && skb_read_tap(g_engine, 0, chunk1 - chunk0, tap_user + (size_t)chunk0 * VOICE_MAX * 2) != SKB_OK)
       shim_die("skb_read_tap");                    /* synth.c:533-611 */
     g_gain_fill = 0;
     g_shim_time[3] += shim_now() - t_f;

@@ -538,6 +538,37 @@ __global__ void __launch_bounds__(SKB_BINW_WARPS * 32) k_render_bins_warp(const 
   if (lane == 0 && na) atomicAdd(a.counter, (unsigned long long)na);
 }
 
+/* Selected columns of the per-voice tap (only the voices being recorded, voice_record[], cross PCIe).
+ * Thread (frame f, voice v): a selected voice's (L, R) goes to the compact out[f][col]; the others only feed the
+ * extremes ext[0] = min(0, samples), ext[1] = max(0, samples) that wire.c's save_wav derives its scale from
+ * (wire.c:150-166 scans EVERY voice of the recording, recorded or not).  Bit patterns of floats >= 0 order like ints,
+ * those of floats <= 0 like reversed unsigned ints: one atomic each. */
+__global__ void k_tap_select(const float2 *__restrict__ tap, int n, int nframes, const int *__restrict__ col_of_voice, int nsel,
+                             float2 *__restrict__ out, unsigned int *__restrict__ ext) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float big = 0.0f, small = 0.0f;
+  if (i < (size_t)n * nframes) {
+    const int v = (int)(i % n);
+    const size_t f = i / n;
+    const float2 t = tap[i];
+    const int c = col_of_voice[v];
+    if (c >= 0) out[f * nsel + c] = t;
+    else {
+      if (t.x > big) big = t.x; if (t.y > big) big = t.y;            /* (a NaN never wins: `g > fbig` is false, wire.c:152) */
+      if (t.x < small) small = t.x; if (t.y < small) small = t.y;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    big = fmaxf(big, __shfl_xor_sync(0xffffffffu, big, d));
+    small = fminf(small, __shfl_xor_sync(0xffffffffu, small, d));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (big > 0.0f) atomicMax(ext + 1, __float_as_uint(big));
+    if (small < 0.0f) atomicMax(ext + 0, __float_as_uint(small));     /* more negative = larger bit pattern */
+  }
+}
+
 /* ======================================================================== */
 /* K4  reduce_rows: partial rows -> raw stereo mix, fixed order              */
 /* ======================================================================== */

@@ -161,3 +161,34 @@ def wex_scenario(s):
     s.wire("/wex300")
     out.append(s.render(1536))
     return np.concatenate(out), s.state()
+
+
+def recording_scenario(s, tmpdir):
+    """`v.. r1` marks voices for recording, `<0.5` starts a recording, `*` stops it and writes skred-<pid>-<ms>.wav through
+    wire.c's save_wav (wire.c:94-185, 698, 816-848; the copy of the per-voice tap into the recording is skred.c:120-131).
+    Eight sounding voices (one FM pair, a muted one), three of them recorded.  Returns the bytes of the WAV file."""
+    import glob
+    s.record_init(1.0)
+    for v in range(8):
+        s.wire("v%d w%d f%d a%.2f p%.1f" % (v, v % 5, 110 * (v + 1), 0.05 + 0.4 * (v % 3), (v - 4) / 5.0))
+    s.wire("v1 F2,3.0")
+    s.wire("v5 m1")
+    s.wire("v6 a2.5")                       # the loudest voice is NOT recorded: save_wav's scale still depends on it
+    for v in (0, 1, 4):
+        s.wire("v%d r1" % v)
+    s.render_recording(1024)
+    s.wire("<0.5")
+    s.render_recording(4 * 512)
+    cwd = os.getcwd()
+    os.chdir(str(tmpdir))
+    try:
+        for f in glob.glob("skred-*.wav"):
+            os.remove(f)
+        s.wire("*")
+        files = glob.glob("skred-*.wav")
+        assert len(files) == 1, files
+        data = open(files[0], "rb").read()
+        os.remove(files[0])
+    finally:
+        os.chdir(cwd)
+    return data

@@ -442,3 +442,17 @@ def test_wex_in_place_table_edit_vs_reference():
     b, sb = cases.wex_scenario(O.DropinCuda(64))
     assert maxdiff(a, b) <= FULL_SCALE_TOL
     assert_state_equal(sa, sb, exact_keys=EXACT)
+
+
+@pytest.mark.parametrize("selective", [0, 1])
+def test_recording_and_save_wav_vs_reference(selective, tmp_path, monkeypatch):
+    """SURVEY 8f N3 on the GPU: `:r` / `<sec` / `*` through the unmodified wire.c over the CUDA drop-in: save_wav's file
+    equals the reference's byte for byte, with the full per-voice tap and with the selective read-back (only the recorded
+    voices' columns cross PCIe: skb_read_tap_selected)."""
+    if not O.have_ref(64):
+        pytest.skip("compiled reference not present")
+    want = cases.recording_scenario(O.RefSkred(64), tmp_path)
+    monkeypatch.setenv("SKB_TAP_SELECTIVE", str(selective))
+    got = cases.recording_scenario(O.DropinCuda(64), tmp_path)
+    assert want[:4] == b"RIFF" and len(want) == 44 + 2048 * 3 * 2 * 2
+    assert got == want

@@ -178,3 +178,18 @@ def test_wex_in_place_table_edit_port_vs_reference():
     assert float(np.max(np.abs(a.astype(np.float64) - b))) <= FULL_SCALE_TOL
     assert float(np.abs(a[1024:]).max()) > 1e-4 and not np.allclose(a[:1024], a[1024:2048])
     assert_state_equal(sa, sb)
+
+
+@pytest.mark.parametrize("selective", [0, 1])
+def test_recording_and_save_wav_port_vs_reference(selective, tmp_path, monkeypatch):
+    """`:r` / `<sec` / `*` through the unmodified wire.c on top of the drop-in.  The WAV file save_wav
+    writes must equal the reference's byte for byte — with the full tap, and with the SELECTIVE read-back in which only
+    the recorded voices' columns (and the extremes of the others) come back from the engine."""
+    import cases
+    if not (O.have_ref(64) and os.path.exists(O.port_lib_path(64))):
+        pytest.skip("oracle libraries not built")
+    want = cases.recording_scenario(O.RefSkred(64), tmp_path)
+    monkeypatch.setenv("SKB_TAP_SELECTIVE", str(selective))
+    got = cases.recording_scenario(O.PortSkred(64), tmp_path)
+    assert len(want) == 44 + 2048 * 3 * 2 * 2 and want[:4] == b"RIFF"
+    assert got == want
