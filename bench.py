@@ -576,6 +576,16 @@ def own_arm(a):
             line["block_latency_ms_p50_64_voices"] = block_latency_small(local, a.latency_blocks)
         if not a.no_cpu:
             line["cpu_baseline"] = cpu_baseline(V)          # rank 0's host, one core, a bounded sample — at every N
+        if world == 1 and not a.no_latency:
+            try:
+                line["modulation_groups"] = modulation_leg(local)
+            except Exception as exc:
+                line["modulation_groups"] = {"unavailable": repr(exc)[:200]}
+        if world == 1 and not a.no_fast:
+            try:
+                line["fast_mode"] = fast_mode_leg(a)
+            except Exception as exc:
+                line["fast_mode"] = {"unavailable": repr(exc)[:200]}
         if world == 1:
             try:
                 line = l2_flushed_headline(line, flushed_act, flushed_ms, a.steps, V, F)
@@ -803,6 +813,141 @@ def weak_scaling_leg(a, local, world, stream, sp, peaks):
     return res
 
 
+def fast_leg_child(a):
+    """Child process of fast_mode_leg: the engine library is whatever SKB_ENGINE_LIB names.  K device-resident steps of the
+    bench workload timed with CUDA events, then the master-volume-scaled mix of 2 more steps dumped for the comparison."""
+    import torch
+    from skred_b200 import Skred
+    from skred_b200.host import load_engine_lib
+    torch.cuda.set_device(0)
+    V, F, LF = a.voices, a.frames, a.launch_frames
+    eng = load_engine_lib()
+    sk = Skred(V, device=0, max_frames=max(F, 512))
+    K = min(a.steps, 40)
+    wl = W.config5(V, seconds=600.0, luts=load_luts(), event_seconds=(K + 12) * F / SR + 1.0, stationary=True)
+    W.install(sk, wl)
+    ev = W.to_skb_events(wl["timed"])
+    sk.lib.skb_shim_queue_events.argtypes = [C.c_void_p, C.c_int]
+    sk.lib.skb_shim_queue_events(ev.ctypes.data, len(ev))
+    sk.flush()
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    sp = C.c_void_p(stream.cuda_stream)
+    d_mix = torch.zeros((F, 2), dtype=torch.float32, device="cuda")
+    sk.lib.skb_shim_render_calls.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    out = np.zeros((2 * F, 2), dtype=np.float32)
+    for i in range(2):                        # the first two steps, through synth(), are the ones compared
+        sk.lib.synth(out[i * F:(i + 1) * F].ctypes.data, None, F, 2, None)
+    for _ in range(3):
+        sk.lib.skb_shim_render_calls(LF, F // LF, d_mix.data_ptr(), sp)
+        sk.lib.skb_shim_discard_gain()
+    torch.cuda.synchronize()
+    eng.skb_sync(sk.engine, sp)
+    a0 = sk.stats().active_voice_frames
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        sk.lib.skb_shim_render_calls(LF, F // LF, d_mix.data_ptr(), sp)
+        sk.lib.skb_shim_discard_gain()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    eng.skb_sync(sk.engine, sp)
+    ms = e0.elapsed_time(e1)
+    act = float(sk.stats().active_voice_frames - a0)
+    eng.skb_backend_name.restype = C.c_char_p
+    np.save(a.fast_dump, out)
+    emit({"backend": eng.skb_backend_name().decode(), "value": act / (ms * 1e-3), "ms_per_step": ms / K, "steps": K,
+          "kernel_ms": float(sk.stats().last_render_ms)})
+    return 0
+
+
+def fast_mode_leg(a):
+    """N = 1 only, reported under its own key: the NON-PARITY build of the engine (FMA contraction on,
+    linearly interpolating oscillator read; skred_b200/fast/libskred_b200.so) on the bench workload, beside the parity
+    build measured the same way in a child process of its own, and the distance between the two renders."""
+    import tempfile
+    from skred_b200 import build as B
+    if not os.path.exists(B.FAST_SO):
+        return {"unavailable": "skred_b200/fast/libskred_b200.so not built"}
+    res = {}
+    with tempfile.TemporaryDirectory() as td:
+        for name, lib in (("parity", B.ENGINE_SO), ("fast", B.FAST_SO)):
+            dump = os.path.join(td, name + ".npy")
+            env = dict(os.environ, SKB_ENGINE_LIB=lib)
+            for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+                env.pop(k, None)
+            cmd = [sys.executable, os.path.abspath(__file__), "--fast-child", "--fast-dump", dump, "--voices", str(a.voices),
+                   "--frames", str(a.frames), "--launch-frames", str(a.launch_frames), "--steps", str(a.steps)]
+            r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=600)
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if r.returncode != 0 or not line:
+                return {"unavailable": "%s child failed (rc %d)" % (name, r.returncode)}
+            res[name] = json.loads(line[-1])
+            res[name]["mix"] = np.load(dump)
+    pa, fa = res["parity"], res["fast"]
+    d = np.abs(pa["mix"].astype(np.float64) - fa["mix"].astype(np.float64))
+    return {"what": "NON-PARITY build: -fmad=true (a*b+c contracted to FMA) and a linearly interpolating table read instead of "
+                    "the reference's truncating one (synth.c:261-274); not used by any parity test or parity number",
+            "backend": fa["backend"], "value": fa["value"], "unit": UNIT, "ms_per_step": fa["ms_per_step"], "steps": fa["steps"],
+            "parity_build_same_measurement": {"backend": pa["backend"], "value": pa["value"], "ms_per_step": pa["ms_per_step"]},
+            "speedup_vs_parity_build": fa["value"] / pa["value"],
+            "max_abs_diff_vs_parity_render": float(d.max()), "rms_diff_vs_parity_render": float(np.sqrt((d ** 2).mean())),
+            "peak_of_parity_render": float(np.abs(pa["mix"]).max()),
+            "compared": "the first %d frames of the workload rendered by both builds through synth()" % len(d)}
+
+
+def modulation_leg(device):
+    """N = 1: the modulated-voice kernels (SURVEY 8d "a sub-variant adds C-modulation pairs to exercise K2"; VERDICT r1
+    item 5).  (a) BASELINE configs[0], 0.sk (a two-voice FM pair): device ms of one 512-frame callback, next to the
+    compiled reference rendering the same callback on one host core; (b) BASELINE configs[2] at 1,024 voices with every
+    voice of a pair CZ-modulating its neighbour: rendered voice-samples/s in 8,192-frame calls.  Both loads are DAGs, so
+    they run through k_render_levels (level_kernel.cuh)."""
+    from skred_b200 import Skred
+    out = {}
+    sk = Skred(64, device=device, private=True, max_frames=8192)
+    sk.apply([("wave_reset", 0, 100), ("wave_set", 0, 0), ("freq_set", 0, 440.0), ("amp_set", 0, 4.0), ("freq_mod_set", 0, 1, 10.0),
+              ("wave_set", 1, 0), ("freq_set", 1, 1.0), ("amp_set", 1, 50.0), ("wave_mute", 1, 1)])
+    buf = np.zeros((512, 2), dtype=np.float32)
+    ms, host = [], []
+    for k in range(300):
+        t0 = time.perf_counter()
+        sk.lib.synth(buf.ctypes.data, None, 512, 2, None)
+        host.append(time.perf_counter() - t0)
+        ms.append(sk.stats().last_render_ms)
+    out["configs0_0sk"] = {"device_ms_per_512_frame_callback": float(np.median(ms[100:])),
+                           "synth_call_ms_p50": float(np.median(host[100:]) * 1e3),
+                           "levelled_voices": int(sk.stats().n_group_voices), "bins": int(sk.stats().n_groups)}
+    sk.lib.synth_free()
+    try:
+        from oracle import oracle as O
+        if O.have_ref(64):
+            ref = O.RefSkred(64, run_seq=False)
+            ref.load_lines(["S100", "v0 w0 f440 a4 F1,10", "v1 w0 f1 a50 m1"])
+            ref.render(50 * 512)
+            t0 = ref.cpu_seconds
+            ref.render(400 * 512)
+            out["configs0_0sk"]["reference_cpu_ms_per_callback_1_core"] = (ref.cpu_seconds - t0) / 400 * 1e3
+    except Exception as exc:
+        out["configs0_0sk"]["reference_cpu_ms_per_callback_1_core"] = None
+        sys.stderr.write("bench.py: 0.sk reference timing skipped: %r\n" % (exc,))
+    V, F = 1024, 8192
+    sk = Skred(V, device=device, private=True, max_frames=F)
+    W.install(sk, W.config3(V, seconds=60.0, cmod_pairs=V // 2))
+    buf = np.zeros((F, 2), dtype=np.float32)
+    ms = []
+    for k in range(24):
+        if k == 8:
+            a0 = sk.stats().active_voice_frames
+        sk.lib.synth(buf.ctypes.data, None, F, 2, None)
+        ms.append(sk.stats().last_render_ms)
+    act = (sk.stats().active_voice_frames - a0) / 16.0
+    med = float(np.median(ms[8:]))
+    out["config3_cmod_pairs"] = {"voices": V, "frames_per_call": F, "device_ms_per_call": med, "value": act / (med * 1e-3), "unit": UNIT,
+                                 "levelled_voices": int(sk.stats().n_group_voices), "bins": int(sk.stats().n_groups)}
+    sk.lib.synth_free()
+    return out
+
+
 def block_latency(sk, nblocks):
     """p50 host-observed time of one synth() call of 512 frames (event flush -> kernels -> 4 KiB D2H)."""
     out = np.zeros((512, 2), dtype=np.float32)
@@ -856,12 +1001,17 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling companion measurement")
+    ap.add_argument("--no-fast", action="store_true", help="N = 1: skip the non-parity fast_mode leg")
+    ap.add_argument("--fast-child", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--fast-dump", default=None, help=argparse.SUPPRESS)
     ap.add_argument("--latency-blocks", type=int, default=1000)
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3
     if not (a.impl == "own" and a.gpus > 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1):
         quiet_stdout()                       # (the torchrun re-launch convenience leaves it to its children)
+    if a.fast_child:
+        return fast_leg_child(a)
     if a.impl == "reference":
         return reference_arm(a)
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -106,6 +106,12 @@ void skb_shim_discard_gain(void);
  * (skb_shim_render_mix x ncalls + skb_shim_flush_render). */
 int skb_shim_render_calls(int frames_per_call, int ncalls, float *d_mix, void *stream);
 
+/* synth() over `num_frames` frames = num_frames / 512 callbacks with the host's per-callback work in between: `between`
+ * is called where skred.c calls seq(frame_count) (skred.c:119), i.e. the sequencer timeline (seq.c:164-213: deferred
+ * wire strings, pattern steps) is walked ahead of the audio and its setter calls are applied at the callback boundaries
+ * of ONE batched launch.  Bit-identical to the loop `synth(512); seq(512);`. */
+void skb_shim_synth_between(float *buffer, int num_frames, int num_channels, void *user, void (*between)(int frame_count));
+
 /* Per-voice tap `user` of synth(): read back only the voices being recorded (voice_record[], wire.c:698) instead of every
  * voice (8 bytes per voice-sample over PCIe).  The other voices' entries stay 0, except one carrier pair per call that
  * holds the extremes save_wav's scale depends on, so the written WAV equals the reference's (synth_shim.c, tests).

@@ -118,6 +118,15 @@ class HarnessSkred(SynthAPI):
         self.lib.ref_render_recording(out.ctypes.data, nframes, block, self.run_seq)
         return out
 
+    def render_batched(self, nframes, call_frames=8192):
+        """The job of render(nframes) with the sequencer running (seq() after every 512-frame callback), handed to the
+        drop-in in calls of `call_frames` frames through skb_shim_synth_between: seq() is walked ahead of the audio."""
+        out = np.zeros((nframes, 2), dtype=np.float32)
+        self.lib.ref_render_batched.argtypes = [C.c_void_p, C.c_long, C.c_int]
+        self.lib.ref_render_batched.restype = C.c_double
+        self.lib.ref_render_batched(out.ctypes.data, nframes, call_frames)
+        return out
+
     def engine_stats(self):
         """skb_stats of the engine behind a drop-in build (port: linked in; cuda: libskred_b200.so)."""
         from skred_b200.host import skb_stats

@@ -190,6 +190,28 @@ double ref_render(float *out, long nframes, int block, int run_seq) {
 
 uint64_t ref_sample_count(void) { return synth_sample_count; }
 
+/* The same job as ref_render(out, nframes, 512, 1) handed to the drop-in as ONE call with seq() as the per-callback hook
+ * (skb_shim_synth_between): the sequencer runs ahead of the audio, the engine batches the callbacks.  The reference
+ * build has no such entry point and runs the plain loop. */
+#ifdef SKB_DROPIN
+#include "skred_b200_shim.h"
+#endif
+static void between_seq(int frame_count) { seq(frame_count); }
+double ref_render_batched(float *out, long nframes, int call_frames) {
+#ifdef SKB_DROPIN
+  long done = 0;
+  while (done < nframes) {
+    int n = (nframes - done) < call_frames ? (int)(nframes - done) : call_frames;
+    skb_shim_synth_between(out + done * 2, n, 2, g_tap, between_seq);
+    done += n;
+  }
+  return 0.0;
+#else
+  (void)call_frames;
+  return ref_render(out, nframes, SYNTH_FRAMES_PER_CALLBACK, 1);
+#endif
+}
+
 /* ---- recording (skred.c:84-131, wire.c `<sec` / `*`): what synth_callback does with the per-voice tap ---- */
 /* synth_callback_init(max_sec), skred.c:93-100, with a test-sized buffer; call before the first ref_render*.
  * The tap is sized for callbacks of `block` frames (synth() latches it on its first call). */

@@ -74,6 +74,22 @@ def build_engine(force=False, verbose=False):
     return ENGINE_SO
 
 
+FAST_SO = os.path.join(HERE, "fast", "libskred_b200.so")
+
+
+def build_engine_fast(force=False):
+    """The NON-PARITY build: FMA contraction on, interpolating oscillator read.  Same soname, its own
+    directory; selected with SKB_ENGINE_LIB (bench.py's fast_mode leg).  No parity test ever loads it."""
+    srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "voice_kernels.cuh", "free_kernel.cuh", "row_kernel.cuh", "level_kernel.cuh", "partition.h")] + [
+        os.path.join(INC, "skred_b200.h"), __file__]
+    if not force and newer(FAST_SO, srcs):
+        return FAST_SO
+    os.makedirs(os.path.dirname(FAST_SO), exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-fmad=false"] + ["-fmad=true", "-DSKB_FAST_MODE=1"]
+    run([NVCC] + flags + ["-I" + INC, "-I" + CSRC, os.path.join(CSRC, "engine.cu"), "-o", FAST_SO])
+    return FAST_SO
+
+
 def build_engine_variant(name, defines):
     """A tuning build of the engine (same soname) under skred_b200/variants/<name>/:
     select it with SKB_ENGINE_LIB=<path>.  defines: e.g. ["-DSKB_SUB=4", "-DSKB_CTA_WARPS=12"]."""
@@ -135,6 +151,7 @@ def build_shim(v, force=False):
 
 def build_all(voices=None, force=False, verbose=False):
     outs = [build_engine(force, verbose)]
+    build_engine_fast(force)
     for v in voices or DEFAULT_VOICES:
         outs.append(build_shim(v, force))
     return outs

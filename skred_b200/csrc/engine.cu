@@ -165,7 +165,11 @@ struct skb_engine {
   cudaEvent_t ev_stage_copied[2] = {nullptr, nullptr}, ev_stage_done[2] = {nullptr, nullptr};
 };
 
+#if SKB_FAST_MODE
+const char *skb_backend_name(void) { return "cuda-sm100a-fast-nonparity"; }
+#else
 const char *skb_backend_name(void) { return "cuda-sm100a"; }
+#endif
 
 static double host_now_us() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return 1e6 * (double)t.tv_sec + 1e-3 * (double)t.tv_nsec; }
 

@@ -50,7 +50,7 @@ __device__ __forceinline__ void lv_phase_block(RowSmem &S, int bi, int nf, int f
   bool ended = false;
   for (int j0 = 0; j0 < nf; j0 += 8) {
     /* the increments of 8 frames do not depend on the phase: off the chain */
-    float g8[8], inc8[8];
+    float g8[8], inc8[8], p8[8];
 #pragma unroll
     for (int t = 0; t < 8; t++) g8[t] = (m.fm != nullptr && !dead && j0 + t < nf) ? __ldg(m.fm + frame0 + j0 + t) : 0.0f;
 #pragma unroll
@@ -60,26 +60,33 @@ __device__ __forceinline__ void lv_phase_block(RowSmem &S, int bi, int nf, int f
     }
 #pragma unroll
     for (int t = 0; t < 8; t++) {
-      const int j = j0 + t;
-      if (j >= nf) break;
-      if (dead) { ph[j][lane] = 0.0f; continue; }
-      float p = phase + inc8[t];                                      /* :226 */
-      float mark = 0.0f;
-      bool fin = false;
-      if (!(fabsf(p) < CUDART_INF_F)) {                               /* :228-232 */
-        p = 0.0f; fin = k.one_shot != 0; mark = CUDART_NAN_F;
-      } else if (p >= k.hi) {                                         /* :242-248 */
-        if (k.stop_at_end) { p = k.hi - 1e-6f; fin = true; }
-        else p = k.lo + wrap_mod(p - k.lo, k.span, k.span2);
-      } else if (p < k.lo) {                                          /* :249-256 */
-        if (k.stop_at_end) { p = k.lo; fin = true; }
-        else p = k.hi - wrap_mod(k.lo - p, k.span, k.span2);
+      float out = 0.0f;
+      if (!dead && j0 + t < nf) {
+        float p = phase + inc8[t];                                    /* :226 */
+        out = p;
+        if (!(p >= k.lo && p < k.hi)) {                               /* rare: a wrap, an end, or a non-finite phase */
+          bool fin = false;
+          if (!(fabsf(p) < CUDART_INF_F)) {                           /* :228-232 */
+            p = 0.0f; fin = k.one_shot != 0; out = CUDART_NAN_F;
+          } else {
+            if (p >= k.hi) {                                          /* :242-248 */
+              if (k.stop_at_end) { p = k.hi - 1e-6f; fin = true; }
+              else p = k.lo + wrap_mod(p - k.lo, k.span, k.span2);
+            } else {                                                  /* :249-256 */
+              if (k.stop_at_end) { p = k.lo; fin = true; }
+              else p = k.hi - wrap_mod(k.lo - p, k.span, k.span2);
+            }
+            out = p;
+          }
+          if (fin) { ended = true; dead = true; }
+        }
+        phase = p;                                                    /* :258 */
+        nv = j0 + t + 1;
       }
-      phase = p;                                                      /* :258 */
-      ph[j][lane] = (mark != 0.0f) ? mark : p;
-      nv = j + 1;
-      if (fin) { ended = true; dead = true; }
+      p8[t] = out;
     }
+#pragma unroll
+    for (int t = 0; t < 8; t++) if (j0 + t < nf) ph[j0 + t][lane] = p8[t];
   }
   S.nval[bi][lane] = nv | (ended ? RP_ENDED : 0);
   const unsigned eb = __ballot_sync(0xffffffffu, ended);

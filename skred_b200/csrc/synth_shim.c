@@ -1163,6 +1163,22 @@ static void tap_read_selected(float *tap_user, int chunk0, int frames) {
   if (chunk0 + frames > g_tap_frames_seen) g_tap_frames_seen = chunk0 + frames;
 }
 
+/* skb_shim_synth_between: the sequencer timeline walked AHEAD of the audio.  The reference's audio callback
+ * is `synth(512 frames); seq(512);` (skred.c:116-119): seq() fires deferred wire strings and pattern steps, which call
+ * the setters, which take effect from the next callback on.  Nothing in seq() depends on the rendered audio, so a batch
+ * host can run it for callback k + 1, k + 2, ... before callback k has left the GPU: this entry point renders
+ * num_frames as callbacks of SYNTH_FRAMES_PER_CALLBACK frames, calls `between(frame_count)` where skred.c calls seq()
+ * after each of them, and finishes ONCE — the engine turns the callbacks into one launch as long as `between` only
+ * produced state edits (triggers, envelope gates, pans), and into a few launches where it changed parameters.
+ * Same audio and state as the callback loop, bit for bit (tests: the shipped pattern patches). */
+static void (*g_between)(int frame_count) = NULL;
+void synth(float *buffer, float *input, int num_frames, int num_channels, void *user);
+void skb_shim_synth_between(float *buffer, int num_frames, int num_channels, void *user, void (*between)(int frame_count)) {
+  g_between = between;
+  synth(buffer, NULL, num_frames, num_channels, user);
+  g_between = NULL;
+}
+
 void synth(float *buffer, float *input, int num_frames, int num_channels, void *user) {
   (void)input;
   /* `user`: the per-voice tap one_skred_frame[frame][voice][L,R], latched on the FIRST call only like the
@@ -1200,6 +1216,10 @@ void synth(float *buffer, float *input, int num_frames, int num_channels, void *
        * is event-free, so one long launch equals many callbacks) */
       const double t_a = shim_now();
       int end = next_firing_boundary(done, num_frames, start_count);
+      if (g_between) {                          /* the host's own seq() runs after every callback: every boundary counts */
+        const int nb = (done / EB + 1) * EB;
+        end = nb < num_frames ? nb : num_frames;
+      }
       const int fires = end <= chunk1;
       if (!fires) end = chunk1;
       if (skb_shim_flush() != SKB_OK) shim_die("flush");
@@ -1213,6 +1233,7 @@ void synth(float *buffer, float *input, int num_frames, int num_channels, void *
       if (fires && n > 0) {
         const int sub = (end % EB) ? (end % EB) : EB;     /* length of the sub-block that just ended */
         fire_due(sub);
+        if (g_between) g_between(sub);          /* skred.c:119: seq(frame_count) right after the callback's synth() */
       }
       done = end;
       /* option: hand the GPU its first callbacks now, so that it renders them while the host fires and queues

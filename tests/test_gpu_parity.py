@@ -456,3 +456,23 @@ def test_recording_and_save_wav_vs_reference(selective, tmp_path, monkeypatch):
     got = cases.recording_scenario(O.DropinCuda(64), tmp_path)
     assert want[:4] == b"RIFF" and len(want) == 44 + 2048 * 3 * 2 * 2
     assert got == want
+
+
+@pytest.mark.parametrize("n", [23, 26, 41, 64])
+def test_sequencer_patch_batched_equals_callbacks(n, golden_patches):
+    """SURVEY 8f N1 on the GPU: the shipped sequencer patches rendered as 8,192-frame calls with seq() walked ahead of the
+    audio (skb_shim_synth_between; the engine batches the 16 callbacks of a call into as few launches as the sequencer's
+    parameter changes allow) against the callback loop on a second engine: state bit for bit, mix within the regrouping
+    of the cross-voice sum, and fewer kernel launches."""
+    lines = patch_lines(golden_patches, n)
+    a, b = O.DropinCuda(64), O.DropinCuda(64)
+    a.load_lines(lines)
+    b.load_lines(lines)
+    frames = 2 * 8192 + 700
+    oa = a.render(frames)
+    la = a.engine_stats().kernel_launches
+    ob = b.render_batched(frames, 8192)
+    lb = b.engine_stats().kernel_launches
+    assert maxdiff(oa, ob) <= 1e-6
+    assert_state_equal(a.state(), b.state(), exact_keys=EXACT)
+    assert lb < la, (la, lb)

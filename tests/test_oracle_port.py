@@ -193,3 +193,23 @@ def test_recording_and_save_wav_port_vs_reference(selective, tmp_path, monkeypat
     got = cases.recording_scenario(O.PortSkred(64), tmp_path)
     assert len(want) == 44 + 2048 * 3 * 2 * 2 and want[:4] == b"RIFF"
     assert got == want
+
+
+@pytest.mark.parametrize("n", [23, 26, 41, 64])
+def test_sequencer_patch_batched_equals_callbacks_port(n, golden_patches):
+    """a patch driven by the pattern sequencer / deferred wire strings (seq.c:164-213) rendered as ONE
+    8,192-frame call with seq() as the per-callback hook (skb_shim_synth_between: the timeline is walked ahead of the
+    audio) equals the callback loop `synth(512); seq(512);` bit for bit — mix and evolving state.  Shim over the CPU
+    restatement; the GPU twin is in tests/test_gpu_parity.py."""
+    if not os.path.exists(O.port_lib_path(64)):
+        pytest.skip("oracle libraries not built")
+    lines = patch_lines(golden_patches, n)
+    a, b = O.PortSkred(64), O.PortSkred(64)
+    a.load_lines(lines)
+    b.load_lines(lines)
+    frames = 2 * 8192 + 700
+    oa = a.render(frames)                       # 512-frame callbacks, seq() after each
+    ob = b.render_batched(frames, 8192)
+    assert np.array_equal(oa.view(np.uint32), ob.view(np.uint32))
+    assert_state_equal(a.state(), b.state())
+    assert n == 64 or float(np.abs(oa).max()) > 0.0       # (64.sk only arms its pattern: it is never started)
