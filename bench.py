@@ -900,7 +900,7 @@ def modulation_leg(device):
     """N = 1: the modulated-voice kernels (SURVEY 8d "a sub-variant adds C-modulation pairs to exercise K2"; VERDICT r1
     item 5).  (a) BASELINE configs[0], 0.sk (a two-voice FM pair): device ms of one 512-frame callback, next to the
     compiled reference rendering the same callback on one host core; (b) BASELINE configs[2] at 1,024 voices with every
-    voice of a pair CZ-modulating its neighbour: rendered voice-samples/s in 8,192-frame calls.  Both loads are DAGs, so
+    voice of a pair CZ-modulating its neighbour: rendered voice-samples/s in 4,096-frame calls.  Both loads are DAGs, so
     they run through k_render_levels (level_kernel.cuh)."""
     from skred_b200 import Skred
     out = {}
@@ -930,7 +930,7 @@ def modulation_leg(device):
     except Exception as exc:
         out["configs0_0sk"]["reference_cpu_ms_per_callback_1_core"] = None
         sys.stderr.write("bench.py: 0.sk reference timing skipped: %r\n" % (exc,))
-    V, F = 1024, 8192
+    V, F = 1024, 4096      # 4,096 frames = one launch (the drop-in's early flush, SKB_EARLY_FLUSH): last_render_ms covers the call
     sk = Skred(V, device=device, private=True, max_frames=F)
     W.install(sk, W.config3(V, seconds=60.0, cmod_pairs=V // 2))
     buf = np.zeros((F, 2), dtype=np.float32)

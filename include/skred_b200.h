@@ -280,6 +280,9 @@ int  skb_comm_init_all(skb_engine *const *engines, int n);
 int  skb_comm_set_mode(skb_engine *e, int mode);
 int  skb_comm_size(const skb_engine *e);          /* ranks of the engine's communicator, 0 = none */
 int  skb_reduce_mix(skb_engine *e, float *d_mix, int nframes, void *stream);
+/* the same for ONE host thread that drives all n engines (skb_comm_init_all): every engine's own mix buffer
+ * (skb_mix_buffer) on its own stream, the n calls inside one NCCL group */
+int  skb_reduce_mix_all(skb_engine *const *engines, int n, int nframes);
 int  skb_comm_destroy(skb_engine *e);
 
 /* Does voice `v` belong to this engine's shard? (world > 1) */

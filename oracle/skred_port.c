@@ -303,6 +303,7 @@ int skb_comm_init_all(skb_engine *const *engines, int n) { (void)engines; (void)
 int skb_comm_set_mode(skb_engine *e, int mode) { (void)e; (void)mode; return SKB_OK; }
 int skb_comm_size(const skb_engine *e) { (void)e; return 0; }
 int skb_comm_destroy(skb_engine *e) { (void)e; return SKB_OK; }
+int skb_reduce_mix_all(skb_engine *const *engines, int n, int nframes) { (void)engines; (void)nframes; return n == 1 ? SKB_OK : SKB_ERR_STATE; }
 int skb_reduce_mix(skb_engine *e, float *d_mix, int nframes, void *stream) {
   (void)d_mix; (void)nframes; (void)stream;
   if (!e) return SKB_ERR_ARG;

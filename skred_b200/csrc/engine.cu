@@ -26,6 +26,7 @@
 #include <time.h>
 
 #include <algorithm>
+#include <cmath>
 #include <queue>
 #include <vector>
 
@@ -531,6 +532,89 @@ static int wait_staging(skb_engine *e) {
   return SKB_OK;
 }
 
+/* deal `items` = (cost, row entry) to at most max_ctas CTAs; returns [ctas][rows_cap], -1 padded.
+ * rank != nullptr: CLASS-AFFINE dealing.  Every distinct loop body a CTA's warps run is code its SM must keep streaming
+ * (each body is 3-6 KB of SASS; one more body per SM measured -20 %, profiles/r01_s4_ab.txt), so the rows of a costly
+ * class (CZ and / or filter) go to a subset of the CTAs sized by the class's share of the costly work — a CTA then
+ * renders ONE costly class — and the light rows (plain, one-shot) fill every CTA up by LPT. */
+static void deal_rows(bool tbl_affine, std::vector<std::pair<int, int>> items, int max_ctas, std::vector<int> &out, int *ctas_out,
+                      int *cap_out, const std::vector<int> *rank, int heavy_cost = 29) {
+      const int n = (int)items.size();
+      const int ctas = std::max(1, std::min(max_ctas, n));
+      const int nb = n ? ((n + ctas - 1) / ctas + SKB_CTA_WARPS - 1) / SKB_CTA_WARPS : 0;
+      const int rcap = nb * SKB_CTA_WARPS;
+      std::stable_sort(items.begin(), items.end(), [](const std::pair<int, int> &x, const std::pair<int, int> &y) { return x.first > y.first; });
+      std::vector<std::vector<std::pair<int, int>>> mine((size_t)ctas);
+      std::vector<long long> load((size_t)ctas, 0);
+      /* LPT of `sub` over CTAs [c0, c1) on top of the current loads */
+      auto lpt = [&](const std::vector<std::pair<int, int>> &sub, int c0, int c1) {
+        typedef std::pair<long long, int> Load;                              /* (load, cta) */
+        std::priority_queue<Load, std::vector<Load>, std::greater<Load>> pqd;
+        for (int c = c0; c < c1; c++) if ((int)mine[c].size() < rcap) pqd.push(Load(load[c], c));
+        std::vector<std::pair<int, int>> left;
+        for (size_t i = 0; i < sub.size(); i++) {
+          if (pqd.empty()) { left.push_back(sub[i]); continue; }
+          Load l = pqd.top(); pqd.pop();
+          mine[l.second].push_back(sub[i]);
+          l.first += sub[i].first; load[l.second] = l.first;
+          if ((int)mine[l.second].size() < rcap) pqd.push(l);                /* a full CTA leaves the heap */
+        }
+        return left;
+      };
+      const int HEAVY = heavy_cost;                                          /* cost_of_rank of anything with CZ or a filter */
+      std::vector<std::pair<int, int>> light;
+      if (rank && ctas >= 8) {
+        std::vector<std::vector<std::pair<int, int>>> byc(8);
+        long long hsum = 0, csum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (size_t i = 0; i < items.size(); i++) {
+          const int rk = (*rank)[items[i].second & ~SKB_ROW_WIDE] & 7;
+          if (items[i].first >= HEAVY) { byc[rk].push_back(items[i]); csum[rk] += items[i].first; hsum += items[i].first; }
+          else light.push_back(items[i]);
+        }
+        int c0 = 0, nheavy = 0, seen = 0;
+        for (int rk = 7; rk >= 0; rk--) nheavy += byc[rk].empty() ? 0 : 1;
+        for (int rk = 7; rk >= 0; rk--) {
+          if (byc[rk].empty()) continue;
+          seen++;
+          int k = (seen == nheavy) ? ctas - c0 : (int)((double)ctas * (double)csum[rk] / (double)hsum + 0.5);
+          k = std::max(1, std::min(k, ctas - c0 - (nheavy - seen)));
+          std::vector<std::pair<int, int>> left;
+          if (tbl_affine) {
+            /* TABLE-AFFINE: consecutive rows of a class hold voices sorted by wave table (feature_key), so a CTA that
+             * renders a CONTIGUOUS run of them sees 1-3 distinct tables and can stage all of them in shared memory
+             * (free_kernel.cuh, SKB_TMA_TABLES); LPT would deal neighbouring rows to different CTAs.  Rows of a class
+             * cost the same (one-shot rows a quarter), so cutting the row-ordered list at equal cost is as balanced. */
+            std::vector<std::pair<int, int>> byrow = byc[rk];
+            std::stable_sort(byrow.begin(), byrow.end(), [](const std::pair<int, int> &x, const std::pair<int, int> &y) {
+              return (x.second & ~SKB_ROW_WIDE) < (y.second & ~SKB_ROW_WIDE); });
+            long long acc = 0;
+            for (size_t i = 0; i < byrow.size(); i++) {
+              int c = c0 + (int)std::min<long long>((long long)k - 1, (acc * k) / std::max<long long>(csum[rk], 1));
+              while (c < c0 + k && (int)mine[c].size() >= rcap) c++;
+              if (c >= c0 + k) { left.push_back(byrow[i]); continue; }
+              mine[c].push_back(byrow[i]); load[c] += byrow[i].first;
+              acc += byrow[i].first;
+            }
+          } else {
+            left = lpt(byc[rk], c0, c0 + k);
+          }
+          light.insert(light.end(), left.begin(), left.end());              /* (did not fit: anywhere) */
+          c0 += k;
+        }
+        std::stable_sort(light.begin(), light.end(), [](const std::pair<int, int> &x, const std::pair<int, int> &y) { return x.first > y.first; });
+      } else {
+        light = items;
+      }
+      lpt(light, 0, ctas);
+      out.assign((size_t)std::max(ctas * rcap, 1), -1);
+      for (int c = 0; c < ctas; c++) {
+        std::stable_sort(mine[c].begin(), mine[c].end(), [](const std::pair<int, int> &x, const std::pair<int, int> &y) {
+          return x.first != y.first ? x.first < y.first : (x.second & ~SKB_ROW_WIDE) < (y.second & ~SKB_ROW_WIDE); });   /* cheapest first: costliest = highest warp id */
+        for (size_t k = 0; k < mine[c].size(); k++) out[(size_t)c * rcap + k] = mine[c][k].second;
+      }
+      *ctas_out = n ? ctas : 0; *cap_out = rcap;
+    }
+
 /* Can the stage pipeline of k_render_levels render this voice (the parameter-only part of lane_needs_generic with
  * levelled = true, free_kernel.cuh)?  What it cannot — S&H, quantize, noise, reverse, smoother off, odd loop windows —
  * keeps the voice's whole component in the frame-lock-step bins. */
@@ -684,8 +768,14 @@ static int replan(skb_engine *e, cudaStream_t st) {
   e->lev_rows.assign((size_t)(max_level + 1), std::make_pair(0, 0));
   e->n_traces = 0;
   {
-    std::stable_sort(lev_voices.begin(), lev_voices.end(), [e](int32_t a2, int32_t b2) {
-      return e->lev_of[a2] != e->lev_of[b2] ? e->lev_of[a2] < e->lev_of[b2] : a2 < b2; });
+    /* inside a level: by feature key like the free voices (a row's lanes then share CZ mode, filter, table: the general
+     * CZ form of the gather stage switches on the mode per lane), then by index; the index rule lives in the references */
+    std::vector<uint64_t> fkey((size_t)n, 0);
+    for (size_t i = 0; i < lev_voices.size(); i++) fkey[lev_voices[i]] = feature_key(&e->par[lev_voices[i]]);
+    std::stable_sort(lev_voices.begin(), lev_voices.end(), [e, &fkey](int32_t a2, int32_t b2) {
+      if (e->lev_of[a2] != e->lev_of[b2]) return e->lev_of[a2] < e->lev_of[b2];
+      if (fkey[a2] != fkey[b2]) return fkey[a2] < fkey[b2];
+      return a2 < b2; });
     int sl = e->n_free_pad;
     for (size_t i = 0; i < lev_voices.size(); i++) {
       const int v = lev_voices[i];
@@ -764,82 +854,7 @@ static int replan(skb_engine *e, cudaStream_t st) {
      * light rows (plain, one-shot) fill every CTA up by LPT as before. */
     const bool tbl_affine = !(getenv("SKB_TBL_AFFINE") && atoi(getenv("SKB_TBL_AFFINE")) == 0);
     auto deal = [tbl_affine](std::vector<std::pair<int, int>> items, int max_ctas, std::vector<int> &out, int *ctas_out, int *cap_out,
-                   const std::vector<int> *rank) {
-      const int n = (int)items.size();
-      const int ctas = std::max(1, std::min(max_ctas, n));
-      const int nb = n ? ((n + ctas - 1) / ctas + SKB_CTA_WARPS - 1) / SKB_CTA_WARPS : 0;
-      const int rcap = nb * SKB_CTA_WARPS;
-      std::stable_sort(items.begin(), items.end(), [](const std::pair<int, int> &x, const std::pair<int, int> &y) { return x.first > y.first; });
-      std::vector<std::vector<std::pair<int, int>>> mine((size_t)ctas);
-      std::vector<long long> load((size_t)ctas, 0);
-      /* LPT of `sub` over CTAs [c0, c1) on top of the current loads */
-      auto lpt = [&](const std::vector<std::pair<int, int>> &sub, int c0, int c1) {
-        typedef std::pair<long long, int> Load;                              /* (load, cta) */
-        std::priority_queue<Load, std::vector<Load>, std::greater<Load>> pqd;
-        for (int c = c0; c < c1; c++) if ((int)mine[c].size() < rcap) pqd.push(Load(load[c], c));
-        std::vector<std::pair<int, int>> left;
-        for (size_t i = 0; i < sub.size(); i++) {
-          if (pqd.empty()) { left.push_back(sub[i]); continue; }
-          Load l = pqd.top(); pqd.pop();
-          mine[l.second].push_back(sub[i]);
-          l.first += sub[i].first; load[l.second] = l.first;
-          if ((int)mine[l.second].size() < rcap) pqd.push(l);                /* a full CTA leaves the heap */
-        }
-        return left;
-      };
-      const int HEAVY = 29;                                                  /* cost_of_rank of anything with CZ or a filter */
-      std::vector<std::pair<int, int>> light;
-      if (rank && ctas >= 8) {
-        std::vector<std::vector<std::pair<int, int>>> byc(8);
-        long long hsum = 0, csum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (size_t i = 0; i < items.size(); i++) {
-          const int rk = (*rank)[items[i].second & ~SKB_ROW_WIDE] & 7;
-          if (items[i].first >= HEAVY) { byc[rk].push_back(items[i]); csum[rk] += items[i].first; hsum += items[i].first; }
-          else light.push_back(items[i]);
-        }
-        int c0 = 0, nheavy = 0, seen = 0;
-        for (int rk = 7; rk >= 0; rk--) nheavy += byc[rk].empty() ? 0 : 1;
-        for (int rk = 7; rk >= 0; rk--) {
-          if (byc[rk].empty()) continue;
-          seen++;
-          int k = (seen == nheavy) ? ctas - c0 : (int)((double)ctas * (double)csum[rk] / (double)hsum + 0.5);
-          k = std::max(1, std::min(k, ctas - c0 - (nheavy - seen)));
-          std::vector<std::pair<int, int>> left;
-          if (tbl_affine) {
-            /* TABLE-AFFINE: consecutive rows of a class hold voices sorted by wave table (feature_key), so a CTA that
-             * renders a CONTIGUOUS run of them sees 1-3 distinct tables and can stage all of them in shared memory
-             * (free_kernel.cuh, SKB_TMA_TABLES); LPT would deal neighbouring rows to different CTAs.  Rows of a class
-             * cost the same (one-shot rows a quarter), so cutting the row-ordered list at equal cost is as balanced. */
-            std::vector<std::pair<int, int>> byrow = byc[rk];
-            std::stable_sort(byrow.begin(), byrow.end(), [](const std::pair<int, int> &x, const std::pair<int, int> &y) {
-              return (x.second & ~SKB_ROW_WIDE) < (y.second & ~SKB_ROW_WIDE); });
-            long long acc = 0;
-            for (size_t i = 0; i < byrow.size(); i++) {
-              int c = c0 + (int)std::min<long long>((long long)k - 1, (acc * k) / std::max<long long>(csum[rk], 1));
-              while (c < c0 + k && (int)mine[c].size() >= rcap) c++;
-              if (c >= c0 + k) { left.push_back(byrow[i]); continue; }
-              mine[c].push_back(byrow[i]); load[c] += byrow[i].first;
-              acc += byrow[i].first;
-            }
-          } else {
-            left = lpt(byc[rk], c0, c0 + k);
-          }
-          light.insert(light.end(), left.begin(), left.end());              /* (did not fit: anywhere) */
-          c0 += k;
-        }
-        std::stable_sort(light.begin(), light.end(), [](const std::pair<int, int> &x, const std::pair<int, int> &y) { return x.first > y.first; });
-      } else {
-        light = items;
-      }
-      lpt(light, 0, ctas);
-      out.assign((size_t)std::max(ctas * rcap, 1), -1);
-      for (int c = 0; c < ctas; c++) {
-        std::stable_sort(mine[c].begin(), mine[c].end(), [](const std::pair<int, int> &x, const std::pair<int, int> &y) {
-          return x.first != y.first ? x.first < y.first : (x.second & ~SKB_ROW_WIDE) < (y.second & ~SKB_ROW_WIDE); });   /* cheapest first: costliest = highest warp id */
-        for (size_t k = 0; k < mine[c].size(); k++) out[(size_t)c * rcap + k] = mine[c][k].second;
-      }
-      *ctas_out = n ? ctas : 0; *cap_out = rcap;
-    };
+                   const std::vector<int> *rank) { deal_rows(tbl_affine, items, max_ctas, out, ctas_out, cap_out, rank); };
     const std::vector<int> *affine = (e->cfg.flags & SKB_CFG_NO_AFFINE) ? nullptr : &row_rank;
     std::vector<std::pair<int, int>> items((size_t)nrows);
     for (int r = 0; r < nrows; r++) items[r] = std::make_pair(row_cost[r], r);
@@ -1183,8 +1198,8 @@ __global__ void k_sum_ranks(const float2 *__restrict__ parts, int nranks, int st
   mix[f] = a;
 }
 
-int skb_reduce_mix(skb_engine *e, float *d_mix, int nframes, void *stream) {
-  if (!e) return SKB_ERR_ARG;
+/* The exchange step in three parts, so that one host thread can put the NCCL calls of all its engines in one group. */
+static int reduce_prepare(skb_engine *e, float *d_mix, int nframes, cudaStream_t st) {
   if (!d_mix || nframes < 0 || nframes > e->cfg.max_frames) return fail(e, SKB_ERR_ARG, "reduce_mix: bad argument");
   cudaSetDevice(e->cfg.device);
   if (batch_launch(e)) return e->err;
@@ -1193,7 +1208,6 @@ int skb_reduce_mix(skb_engine *e, float *d_mix, int nframes, void *stream) {
     return fail(e, SKB_ERR_STATE, "reduce_mix: world > 1 and no communicator (skb_comm_init_rank / skb_comm_init_all)");
   }
   if (e->comm_n == 1 || nframes == 0) return e->err;
-  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
   /* A caller may run the exchange on a stream of its own so that it overlaps the next render: the reduce is then
    * ordered after everything queued on the render stream so far by an event (no host synchronisation, and the
    * engine keeps launching on its render stream); making the NEXT writer of d_mix wait for `stream` is the caller's. */
@@ -1203,29 +1217,70 @@ int skb_reduce_mix(skb_engine *e, float *d_mix, int nframes, void *stream) {
   } else if (!e->last_stream) {
     e->last_stream = st;
   }
+  if (e->comm_mode == SKB_COMM_ORDERED && e->comm_rank == 0 && (size_t)e->comm_n * e->cfg.max_frames > e->gather_cap) {
+    CK(cudaStreamSynchronize(st));
+    cudaError_t r = grow_dev(&e->d_gather, &e->gather_cap, (size_t)e->comm_n * e->cfg.max_frames);
+    if (r != cudaSuccess) return fail(e, SKB_ERR_CUDA, "gather alloc", cudaGetErrorString(r));
+  }
+  return e->err;
+}
+
+static int reduce_enqueue(skb_engine *e, float *d_mix, int nframes, cudaStream_t st) {
+  if (!e->comm || e->comm_n == 1 || nframes == 0) return e->err;
+  cudaSetDevice(e->cfg.device);
   if (e->comm_mode == SKB_COMM_NCCL_REDUCE) {
     NK(g_nccl.Reduce(d_mix, d_mix, (size_t)nframes * 2, ncclFloat32, ncclSum, 0, e->comm, st));
-  } else {
+  } else if (e->comm_rank == 0) {
     const int mf = e->cfg.max_frames;
-    if (e->comm_rank == 0) {
-      if ((size_t)e->comm_n * mf > e->gather_cap) {
-        CK(cudaStreamSynchronize(st));
-        cudaError_t r = grow_dev(&e->d_gather, &e->gather_cap, (size_t)e->comm_n * mf);
-        if (r != cudaSuccess) return fail(e, SKB_ERR_CUDA, "gather alloc", cudaGetErrorString(r));
-      }
-      CK(cudaMemcpyAsync(e->d_gather, d_mix, (size_t)nframes * sizeof(float2), cudaMemcpyDeviceToDevice, st));
-      NK(g_nccl.GroupStart());
-      for (int r = 1; r < e->comm_n; r++)
-        NK(g_nccl.Recv(e->d_gather + (size_t)r * mf, (size_t)nframes * 2, ncclFloat32, r, e->comm, st));
-      NK(g_nccl.GroupEnd());
-      k_sum_ranks<<<(nframes + 255) / 256, 256, 0, st>>>(e->d_gather, e->comm_n, mf, (float2 *)d_mix, nframes);
-      e->stats.kernel_launches++;
-    } else {
-      NK(g_nccl.Send(d_mix, (size_t)nframes * 2, ncclFloat32, 0, e->comm, st));
-    }
+    NK(g_nccl.GroupStart());
+    for (int r = 1; r < e->comm_n; r++)
+      NK(g_nccl.Recv(e->d_gather + (size_t)r * mf, (size_t)nframes * 2, ncclFloat32, r, e->comm, st));
+    NK(g_nccl.GroupEnd());
+  } else {
+    NK(g_nccl.Send(d_mix, (size_t)nframes * 2, ncclFloat32, 0, e->comm, st));
+  }
+  return e->err;
+}
+
+static int reduce_complete(skb_engine *e, float *d_mix, int nframes, cudaStream_t st) {
+  if (!e->comm || e->comm_n == 1 || nframes == 0) return e->err;
+  cudaSetDevice(e->cfg.device);
+  if (e->comm_mode == SKB_COMM_ORDERED && e->comm_rank == 0) {
+    /* rank 0's own partial sum is row 0; then rank 1, 2, ... in that order (k_sum_ranks) */
+    const int mf = e->cfg.max_frames;
+    CK(cudaMemcpyAsync(e->d_gather, d_mix, (size_t)nframes * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    k_sum_ranks<<<(nframes + 255) / 256, 256, 0, st>>>(e->d_gather, e->comm_n, mf, (float2 *)d_mix, nframes);
+    e->stats.kernel_launches++;
   }
   CK(cudaGetLastError());
   return e->err;
+}
+
+int skb_reduce_mix(skb_engine *e, float *d_mix, int nframes, void *stream) {
+  if (!e) return SKB_ERR_ARG;
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  if (reduce_prepare(e, d_mix, nframes, st)) return e->err;
+  if (reduce_enqueue(e, d_mix, nframes, st)) return e->err;
+  return reduce_complete(e, d_mix, nframes, st);
+}
+
+/* One host thread, several engines (skb_comm_init_all): NCCL wants the ranks' calls of one collective inside a group.
+ * Every engine reduces its own mix buffer (skb_mix_buffer) on its own stream. */
+int skb_reduce_mix_all(skb_engine *const *engines, int n, int nframes) {
+  if (!engines || n < 1 || !engines[0]) return SKB_ERR_ARG;
+  skb_engine *e = engines[0];
+  for (int r = 0; r < n; r++) {
+    if (!engines[r]) return fail(e, SKB_ERR_ARG, "reduce_mix_all: null engine");
+    if (n > 1 && !engines[r]->comm) return fail(e, SKB_ERR_STATE, "reduce_mix_all: engine without a communicator");
+    if (reduce_prepare(engines[r], (float *)engines[r]->d_mix, nframes, engines[r]->stream)) return engines[r]->err;
+  }
+  if (n == 1) return e->err;
+  NK(g_nccl.GroupStart());
+  int rc = SKB_OK;
+  for (int r = 0; r < n && rc == SKB_OK; r++) rc = reduce_enqueue(engines[r], (float *)engines[r]->d_mix, nframes, engines[r]->stream);
+  NK(g_nccl.GroupEnd());
+  for (int r = 0; r < n && rc == SKB_OK; r++) rc = reduce_complete(engines[r], (float *)engines[r]->d_mix, nframes, engines[r]->stream);
+  return rc;
 }
 
 int skb_owns_voice(skb_engine *e, int voice) {

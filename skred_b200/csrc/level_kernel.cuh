@@ -41,6 +41,19 @@ struct LevSmem {
 
 __host__ __device__ inline size_t skb_levels_smem_bytes() { return sizeof(LevSmem); }
 
+/* the rare branch of osc_next (synth.c:228-256), out of line so that the 32 unrolled frames of a block stay small:
+ * a non-finite phase (reset to 0, the sample of that frame is the literal 0.0f: flag 2), a wrap in either direction, or
+ * the end of a one-shot (flag 1). */
+__device__ __noinline__ float lv_phase_rare(float p, float lo, float hi, float span, float span2, int stop_at_end, int one_shot, int *flags) {
+  if (!(fabsf(p) < CUDART_INF_F)) { *flags = 2 | (one_shot ? 1 : 0); return 0.0f; }     /* :228-232 */
+  if (p >= hi) {                                                                           /* :242-248 */
+    if (stop_at_end) { *flags = 1; return hi - 1e-6f; }
+    return lo + wrap_mod(p - lo, span, span2);
+  }
+  if (stop_at_end) { *flags = 1; return lo; }                                              /* :249-256 */
+  return hi - wrap_mod(lo - p, span, span2);
+}
+
 /* A: phases of one block, osc_next (synth.c:217-258) in full: FM increment, !isfinite guard, both wrap directions,
  * one-shot end.  A NaN in ph[] marks a frame whose oscillator output is the literal 0.0f (:228-232). */
 __device__ __forceinline__ void lv_phase_block(RowSmem &S, int bi, int nf, int frame0, const VoiceK &k, float inc0, const LevMods &m,
@@ -48,45 +61,32 @@ __device__ __forceinline__ void lv_phase_block(RowSmem &S, int bi, int nf, int f
   float (*ph)[32] = S.ph[bi];
   int nv = 0;
   bool ended = false;
-  for (int j0 = 0; j0 < nf; j0 += 8) {
-    /* the increments of 8 frames do not depend on the phase: off the chain */
-    float g8[8], inc8[8], p8[8];
+  /* the increments of the block's frames do not depend on the phase: all of the modulator's samples are requested first
+   * (one L2 round trip per block, not per 8 frames), the increments follow off the chain */
+  float inc[RP_FB];
 #pragma unroll
-    for (int t = 0; t < 8; t++) g8[t] = (m.fm != nullptr && !dead && j0 + t < nf) ? __ldg(m.fm + frame0 + j0 + t) : 0.0f;
+  for (int t = 0; t < RP_FB; t++) inc[t] = (m.fm != nullptr && !dead && t < nf) ? __ldg(m.fm + frame0 + t) : 0.0f;
 #pragma unroll
-    for (int t = 0; t < 8; t++) {
-      const float g = g8[t] * m.fm_depth;                             /* :553 */
-      inc8[t] = (m.fm != nullptr) ? inc0 + (m.fm_prod * g) : inc0;    /* :554 */
-    }
+  for (int t = 0; t < RP_FB; t++) {
+    const float g = inc[t] * m.fm_depth;                              /* :553 */
+    inc[t] = (m.fm != nullptr) ? inc0 + (m.fm_prod * g) : inc0;       /* :554 */
+  }
 #pragma unroll
-    for (int t = 0; t < 8; t++) {
-      float out = 0.0f;
-      if (!dead && j0 + t < nf) {
-        float p = phase + inc8[t];                                    /* :226 */
-        out = p;
-        if (!(p >= k.lo && p < k.hi)) {                               /* rare: a wrap, an end, or a non-finite phase */
-          bool fin = false;
-          if (!(fabsf(p) < CUDART_INF_F)) {                           /* :228-232 */
-            p = 0.0f; fin = k.one_shot != 0; out = CUDART_NAN_F;
-          } else {
-            if (p >= k.hi) {                                          /* :242-248 */
-              if (k.stop_at_end) { p = k.hi - 1e-6f; fin = true; }
-              else p = k.lo + wrap_mod(p - k.lo, k.span, k.span2);
-            } else {                                                  /* :249-256 */
-              if (k.stop_at_end) { p = k.lo; fin = true; }
-              else p = k.hi - wrap_mod(k.lo - p, k.span, k.span2);
-            }
-            out = p;
-          }
-          if (fin) { ended = true; dead = true; }
-        }
-        phase = p;                                                    /* :258 */
-        nv = j0 + t + 1;
+  for (int t = 0; t < RP_FB; t++) {
+    float out = 0.0f;
+    if (!dead && t < nf) {
+      float p = phase + inc[t];                                       /* :226 */
+      out = p;
+      if (!(p >= k.lo && p < k.hi)) {                                 /* rare: a wrap, an end, or a non-finite phase */
+        int fl = 0;
+        p = lv_phase_rare(p, k.lo, k.hi, k.span, k.span2, k.stop_at_end ? 1 : 0, k.one_shot, &fl);
+        out = (fl & 2) ? CUDART_NAN_F : p;
+        if (fl & 1) { ended = true; dead = true; }
       }
-      p8[t] = out;
+      phase = p;                                                      /* :258 */
+      nv = t + 1;
     }
-#pragma unroll
-    for (int t = 0; t < 8; t++) if (j0 + t < nf) ph[j0 + t][lane] = p8[t];
+    ph[t][lane] = out;
   }
   S.nval[bi][lane] = nv | (ended ? RP_ENDED : 0);
   const unsigned eb = __ballot_sync(0xffffffffu, ended);
@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(RP_THREADS) k_render_levels(const __grid_const
     }
     const bool any_live = __any_sync(0xffffffffu, !dead);
     const bool generic = __any_sync(0xffffffffu, !dead && cls == 7);
+    if (tid == 0 && any_live) atomicAdd(a.counters + 2 + (generic ? 7 : 6), 1ull);   /* diagnostics: segments per path (class_rows[6] staged, [7] generic) */
 
     if (!any_live) {
       for (int f = tid; f < nfr; f += RP_THREADS) orow[f0 + f] = make_float2(0.0f, 0.0f);
@@ -355,6 +356,7 @@ __global__ void __launch_bounds__(RP_THREADS) k_render_levels(const __grid_const
       bool deadA = dead;
       __syncthreads();
       for (int t = 0; t < nb + 3; t++) {
+        const long long t_s0 = clock64();
         if (roleA) {
           if (t < nb) {
             if (row_fm) lv_phase_block(S, t & (RP_NBUF - 1), min(RP_FB, nfr - t * RP_FB), t * RP_FB, kk, p.inc, m, phase, deadA, lane);
@@ -422,7 +424,13 @@ __global__ void __launch_bounds__(RP_THREADS) k_render_levels(const __grid_const
             }
           }
         }
+        const long long t_s1 = clock64();
         __syncthreads();
+        if (lane == 0 && (warp == 0 || warp == 1 || roleC)) {      /* diagnostics (skb_stats.phase_cycles): work and wait per stage */
+          const int kx = roleA ? 0 : (roleC ? 2 : 1);
+          atomicAdd(a.counters + 10 + kx, (unsigned long long)(t_s1 - t_s0));
+          atomicAdd(a.counters + 13 + kx, (unsigned long long)(clock64() - t_s1));
+        }
       }
       if (roleA) S.fphase[lane] = phase;
       __syncthreads();

@@ -115,6 +115,8 @@ int skb_shim_configure(int device, int rank, int world, int max_frames) {
   return SKB_OK;
 }
 
+static int g_user_slots[WAVE_TABLE_MAX], g_n_user_slots = 0;   /* user slots that have a device copy (the ones to watch) */
+static unsigned char g_user_slot_listed[WAVE_TABLE_MAX];
 static skb_engine *engine(void) {
   if (g_engine) return g_engine;
   skb_config cfg;
@@ -139,6 +141,8 @@ static skb_engine *engine(void) {
     abort();
   }
   for (int i = 0; i < WAVE_TABLE_MAX; i++) g_slot_tid[i] = -1;
+  g_n_user_slots = 0;
+  memset(g_user_slot_listed, 0, sizeof(g_user_slot_listed));
   for (int v = 0; v < VOICE_MAX; v++) g_voice_tid[v] = -1;
   return g_engine;
 }
@@ -192,14 +196,16 @@ static int32_t slot_table_id(int wave) {
   g_slot_size[wave] = wave_size[wave];
   g_slot_tid[wave] = tid;
   g_slot_fp[wave] = slot_fingerprint(wave);
+  if (wave >= EXT_SAMPLE_000 && !g_user_slot_listed[wave]) { g_user_slot_listed[wave] = 1; g_user_slots[g_n_user_slots++] = wave; }
   return tid;
 }
 
 /* Called at every block boundary: a user slot (EXT_SAMPLE_000 ... 999) whose data changed under the same pointer is
  * uploaded again and every voice that plays it is re-pointed — the reference reads the edited floats from the next
- * frame on (its table IS the edited array).  ~800 compares per call when nothing is loaded. */
+ * frame on (its table IS the edited array).  One 64-sample fingerprint per uploaded user slot per call. */
 static void refresh_edited_tables(void) {
-  for (int wave = EXT_SAMPLE_000; wave < WAVE_TABLE_MAX; wave++) {
+  for (int k = 0; k < g_n_user_slots; k++) {
+    const int wave = g_user_slots[k];
     if (g_slot_tid[wave] < 0 || g_slot_ptr[wave] != wave_table_data[wave] || g_slot_size[wave] != wave_size[wave]) continue;
     if (slot_fingerprint(wave) == g_slot_fp[wave]) continue;
     g_slot_tid[wave] = -1;

@@ -31,6 +31,8 @@ def run(name, sk, frames, calls=40):
     print("%-44s %d frames per call: device %.4f ms per call (%.4f ms per 512 frames), %.3g rendered voice-samples/s, "
           "%d group voices in %d bins, %d free" % (name, frames, med, med * 512 / frames, act / (med * 1e-3),
                                                     st.n_group_voices, st.n_groups, st.n_free_voices), flush=True)
+    print("      segments [staged, generic] = %s; stage clocks us [A, G, C work | A, G, C wait] summed over CTAs and launches: %s" %
+          (list(st.class_rows[6:8]), ["%.0f" % (x / 1965.0) for x in st.phase_cycles[:6]]), flush=True)
     sk.lib.synth_free()
 
 

@@ -1,5 +1,6 @@
 #!/bin/bash
-# round 2: the whole GPU suite, smoke, both bench arms, launch list, one full ncu capture of the dominant kernel
+# round 2, one GPU: the whole GPU suite, smoke, the modulated-voice probe, both bench arms, the launch list of the bench command.
+# (The one `ncu --set full` capture of the dominant kernel is tools/gpu_r2_capture.sh, a call of its own.)
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/gpu.txt 2>&1; nproc >> gpurun_out/gpu.txt
 ( time timeout 1700 python -m pytest tests -m gpu -q ) > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
@@ -11,5 +12,4 @@ timeout 600 python bench.py --steps 20 --warmup 5 2>gpurun_out/bench.err > gpuru
 NARGS="--steps 2 --warmup 3 --no-cpu --no-latency --no-fast --min-timed-s 0"
 timeout 300 python bench.py $NARGS > gpurun_out/plain.log 2>&1 &&
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py $NARGS > gpurun_out/ncu1.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_render_free -s 6 -c 1 -o gpurun_out/prof -f python bench.py $NARGS > gpurun_out/ncu2.log 2>&1
-tail -2 gpurun_out/ncu2.log
+tail -2 gpurun_out/ncu1.log | cut -c1-300

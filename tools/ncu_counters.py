@@ -2,7 +2,8 @@
 """Write profiles/r02_ncu_counters.json from one `ncu --set full` capture of the dominant kernel of the bench workload:
 DRAM bytes and warp instructions of ONE launch, stamped with the hash of the kernel sources the capture was taken from.
 bench.py reports roofline.traffic / roofline_issue from this file ONLY while that hash still matches the tree.
-  python tools/ncu_counters.py gpurun_out/prof.ncu-rep [voices_on_gpu] [frames]"""
+  python tools/ncu_counters.py gpurun_out/prof.ncu-rep [voices_on_gpu] [frames] [out.json]
+Run it ON THE GPU BOX right after the capture (tools/gpu_r2_full.sh does), so the hash is that of the tree the capture ran."""
 import csv
 import io
 import json
@@ -47,6 +48,6 @@ out = {
     "sm_cycles_elapsed_max": val("sm__cycles_elapsed.max"),
     "duration_us_under_ncu": val("gpu__time_duration.sum") / (1000.0 if rows[1][hdr.index("gpu__time_duration.sum")] in ("nsecond", "ns") else 1.0),
 }
-p = os.path.join(ROOT, "profiles", "r02_ncu_counters.json")
+p = sys.argv[4] if len(sys.argv) > 4 else os.path.join(ROOT, "profiles", "r02_ncu_counters.json")
 json.dump(out, open(p, "w"), indent=1)
 print(json.dumps(out))
