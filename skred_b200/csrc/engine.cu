@@ -72,6 +72,13 @@ struct skb_engine {
   std::vector<uint64_t> edge_sig;                   /* per voice: hash of its live edges (re-plan trigger) */
   int n_free = 0, n_free_pad = 0, n_slots = 0, n_free_rows = 0, max_bin_threads = 0;
   int n_small_bins = 0;              /* bins [0, n_small_bins) hold <= 32 voices each (k_render_bins_warp), the rest one big component each */
+  int n_big_end = 0;                 /* bins [n_small_bins, n_big_end): one component of 33 ... 1,024 voices (k_render_bins); [n_big_end, size()):
+                                        cyclic components above that (k_render_bins_huge) */
+  float *d_binx = nullptr; size_t binx_cap = 0;      /* voice_sample exchange of the huge bins: [3][cap] floats */
+  /* How many envelopes are in a transient, roughly: envelope triggers / releases seen, halved every 0.5 s of audio.  Only
+   * picks the shared-memory size of the free-voice kernels (free_kernel.cuh: SKB_ENV_WARP_FLOATS_*), never a result. */
+  double env_activity = 0.0; long env_ops_pending = 0;
+  int env_floats_forced = 0;         /* $SKB_ENV_FLOATS: testing aid */
   int rows_cap = 0;                  /* entries per CTA in d_ctarows */
   int *d_ctarows = nullptr; size_t ctarows_cap = 0;
   std::vector<int> h_ctarows;
@@ -110,7 +117,6 @@ struct skb_engine {
   std::vector<TableDesc> tables;
   skb_bin_desc *d_bins = nullptr; int d_bins_cap = 0;
   float2 *d_partials = nullptr; size_t partials_cap = 0;
-  float *d_envbuf = nullptr; size_t envbuf_cap = 0;   /* envelope pre-pass rows: [CTA][thread][SKB_ENV_WIN] */
   float2 *d_part2 = nullptr;
   unsigned int *d_tickets = nullptr;
   unsigned long long *d_counters = nullptr, *h_counters = nullptr;
@@ -285,6 +291,7 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
    * launch of 8,192 voices, slower from 16,384 voices up — not enough to switch by default: opt-in */
   e->rows_mode = (cfg->flags & SKB_CFG_ROWS) ? 1 : 0;
   e->rows_auto_max = 2 * e->n_sm;
+  { const char *s = getenv("SKB_ENV_FLOATS"); if (s && s[0]) { const int v = atoi(s); if (v >= SKB_ENV_WARP_FLOATS_SMALL && v <= SKB_ENV_WARP_FLOATS_LARGE) e->env_floats_forced = v & ~3; } }
   { const char *s = getenv("SKB_ROWS"); if (s && s[0]) e->rows_mode = atoi(s);
     s = getenv("SKB_ROWS_MAX"); if (s && s[0]) e->rows_auto_max = atoi(s); }
   memset(&e->stats, 0, sizeof(e->stats));
@@ -326,13 +333,13 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
             cudaEventCreateWithFlags(&e->ev_stage_done[0], cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_stage_done[1], cudaEventDisableTiming) == cudaSuccess &&
             cudaFuncSetAttribute(k_render_free, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)skb_free_smem_bytes()) == cudaSuccess &&
+                                 (int)skb_free_smem_bytes(SKB_ENV_WARP_FLOATS_LARGE)) == cudaSuccess &&
             cudaFuncSetAttribute(k_render_free_tap, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)skb_free_smem_bytes()) == cudaSuccess &&
+                                 (int)skb_free_smem_bytes(SKB_ENV_WARP_FLOATS_LARGE)) == cudaSuccess &&
             cudaFuncSetAttribute(k_render_window, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)skb_free_smem_bytes()) == cudaSuccess &&
+                                 (int)skb_free_smem_bytes(SKB_ENV_WARP_FLOATS_LARGE)) == cudaSuccess &&
             cudaFuncSetAttribute(k_render_biquad, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)skb_free_smem_bytes()) == cudaSuccess &&
+                                 (int)skb_free_smem_bytes(SKB_ENV_WARP_FLOATS_LARGE)) == cudaSuccess &&
             cudaFuncSetAttribute(k_render_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)skb_rows_smem_bytes()) == cudaSuccess &&
             cudaFuncSetAttribute(k_render_levels, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -365,10 +372,10 @@ void skb_destroy(skb_engine *e) {
   skb_comm_destroy(e);
   cudaFree(e->d_gather); cudaFree(e->d_mig); cudaFree(e->d_migidx); cudaFree(e->d_trace);
   cudaFree(e->d_pq); cudaFree(e->d_sq[0]); cudaFree(e->d_sq[1]); cudaFree(e->d_tables);
-  cudaFree(e->d_bins); cudaFree(e->d_partials); cudaFree(e->d_mix); cudaFree(e->d_out);
+  cudaFree(e->d_bins); cudaFree(e->d_binx); cudaFree(e->d_partials); cudaFree(e->d_mix); cudaFree(e->d_out);
   cudaFree(e->d_gain); cudaFree(e->d_noise); cudaFree(e->d_idx); cudaFree(e->d_recs);
   cudaFree(e->d_ops); cudaFree(e->d_runs); cudaFree(e->d_vsnap);
-  cudaFree(e->d_envbuf); cudaFree(e->d_ctarows); cudaFree(e->d_ctaphase);
+  cudaFree(e->d_ctarows); cudaFree(e->d_ctaphase);
   for (int i = 0; i < 2; i++) {
     cudaFree(e->d_stage[i]); cudaFreeHost(e->h_stage[i]);
     if (e->ev_stage_copied[i]) cudaEventDestroy(e->ev_stage_copied[i]);
@@ -429,6 +436,7 @@ int skb_set_params(skb_engine *e, int voice, const skb_voice_params *p) {
 int skb_push_ops(skb_engine *e, const skb_op *ops, int n) {
   if (!e || n < 0 || (n > 0 && !ops)) return fail(e, SKB_ERR_ARG, "push_ops: bad argument");
   e->ops.insert(e->ops.end(), ops, ops + n);
+  for (int i = 0; i < n; i++) e->env_ops_pending += (ops[i].code == SKB_OP_ENV_ON || ops[i].code == SKB_OP_ENV_OFF);
   return SKB_OK;
 }
 
@@ -792,18 +800,19 @@ static int replan(skb_engine *e, cudaStream_t st) {
   }
   /* components of <= 32 voices are packed into bins of <= 32 and rendered one WARP per bin (k_render_bins_warp, batched
    * launches with in-kernel boundary ops); a larger component gets a CTA of its own (k_render_bins) */
-  std::vector<std::vector<int32_t>> binv, binv_big;
+  std::vector<std::vector<int32_t>> binv, binv_big, binv_huge;
   for (size_t i = 0; i < roots.size(); i++) {
     const int sz = (int)members[i].size();
     if (sz == 0) continue;                                  /* levelled */
-    if (sz > SKB_BIN_MAX)
-      return fail(e, SKB_ERR_CAPACITY, "a modulation group has more than 1024 voices");
+    if (sz > SKB_BIN_MAX) { binv_huge.push_back(members[i]); continue; }       /* legal in the reference: rendered, slowly */
     if (sz > SKB_BIN_WARP) { binv_big.push_back(members[i]); continue; }
     if (binv.empty() || (int)binv.back().size() + sz > SKB_BIN_WARP) binv.push_back(std::vector<int32_t>());
     binv.back().insert(binv.back().end(), members[i].begin(), members[i].end());
   }
   e->n_small_bins = (int)binv.size();
   binv.insert(binv.end(), binv_big.begin(), binv_big.end());
+  e->n_big_end = (int)binv.size();
+  binv.insert(binv.end(), binv_huge.begin(), binv_huge.end());
   int slot = e->n_lev_pad;
   e->n_free_rows = e->n_free_pad / 32;
   /* partial-row groups: one per (CTA, batch) of k_render_free, then the bins 16 to a group */
@@ -944,7 +953,7 @@ static int replan(skb_engine *e, cudaStream_t st) {
       d.nlevels = std::max(d.nlevels, lv + 1);
     }
     e->bins.push_back(d);
-    if ((int)b >= e->n_small_bins) e->max_bin_threads = std::max(e->max_bin_threads, (d.size + 31) & ~31);
+    if ((int)b >= e->n_small_bins && (int)b < e->n_big_end) e->max_bin_threads = std::max(e->max_bin_threads, (d.size + 31) & ~31);
     slot += d.size;
   }
   e->n_slots = slot;
@@ -989,6 +998,10 @@ static int replan(skb_engine *e, cudaStream_t st) {
     /* pageable source: synchronous with respect to the host, ordered on st */
     CK(cudaMemcpyAsync(e->d_bins, e->bins.data(), e->bins.size() * sizeof(skb_bin_desc), cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
+    if ((int)e->bins.size() > e->n_big_end) {
+      cudaError_t rx = grow_dev(&e->d_binx, &e->binx_cap, (size_t)3 * e->cap);
+      if (rx != cudaSuccess) return fail(e, SKB_ERR_CUDA, "huge-bin exchange alloc", cudaGetErrorString(rx));
+    }
   }
   {
     cudaError_t rr;
@@ -999,8 +1012,6 @@ static int replan(skb_engine *e, cudaStream_t st) {
     e->h_ctarows = ctarows;
     rr = grow_dev(&e->d_ctaphase, &e->ctaphase_cap, (size_t)std::max(e->n_sm, 1) * (8 + SKB_CTA_WARPS));
     if (rr != cudaSuccess) return fail(e, SKB_ERR_CUDA, "phase clock alloc", cudaGetErrorString(rr));
-    rr = grow_dev(&e->d_envbuf, &e->envbuf_cap, (size_t)std::max(e->n_sm, 1) * SKB_CTA_THREADS * SKB_ENV_WIN);   /* per CTA of any pass */
-    if (rr != cudaSuccess) return fail(e, SKB_ERR_CUDA, "envelope scratch alloc", cudaGetErrorString(rr));
   }
   /* every owned voice gets a fresh record */
   std::fill(e->noise_flag.begin(), e->noise_flag.end(), 0);
@@ -1420,7 +1431,16 @@ static int batch_launch(skb_engine *e) {
     fa.win_frames = d_winp; fa.win_ob = d_winp + nwin; fa.nwin = nwin; fa.ob_stride = nbk + 1;
     fa.bops = d_bopsp; fa.wake = d_wake;
     fa.ctarows = e->d_partials; fa.row_stride = nframes;
-    fa.envbuf = e->d_envbuf; fa.counters = e->d_counters; fa.cta_phase = e->d_ctaphase;
+    fa.envbuf = nullptr; fa.counters = e->d_counters; fa.cta_phase = e->d_ctaphase;
+    {
+      /* envelope triggers / releases of this launch join the running count; a quarter of the voices in a transient asks
+       * for the long envelope slices (more shared memory, less L1) */
+      e->env_activity = e->env_activity * exp2(-(double)nframes / 22050.0) + (double)e->env_ops_pending;
+      e->env_ops_pending = 0;
+      const bool many = e->env_activity > 0.25 * (double)std::max(e->n_free, 1);
+      fa.env_warp_floats = e->env_floats_forced ? e->env_floats_forced : (many ? SKB_ENV_WARP_FLOATS_LARGE : SKB_ENV_WARP_FLOATS_SMALL);
+    }
+    const size_t free_smem = skb_free_smem_bytes(fa.env_warp_floats);
     fa.force_generic = (e->cfg.flags & SKB_CFG_FORCE_GENERIC) ? 1 : 0;
     fa.wide_on = wide ? 1 : 0;
     fa.snap = e->d_snap; fa.snap_nwin = e->snap_nwin;
@@ -1435,22 +1455,22 @@ static int batch_launch(skb_engine *e) {
       fa.group0 = e->n_prows;
       k_render_rows<<<e->n_free_rows, RP_THREADS, skb_rows_smem_bytes(), st>>>(fa);
       e->stats.rows_launches++;
-    } else if (e->tap_on) k_render_free_tap<<<e->free_ctas, SKB_CTA_THREADS, skb_free_smem_bytes(), st>>>(fa);
-    else k_render_free<<<e->free_ctas, SKB_CTA_THREADS, skb_free_smem_bytes(), st>>>(fa);
+    } else if (e->tap_on) k_render_free_tap<<<e->free_ctas, SKB_CTA_THREADS, free_smem, st>>>(fa);
+    else k_render_free<<<e->free_ctas, SKB_CTA_THREADS, free_smem, st>>>(fa);
     e->stats.kernel_launches++;
     if (wide) {
       CK(cudaEventRecord(e->ev_a, st));
       FreeArgs fb = fa;
       fb.wide_on = 0; fb.bops = nullptr; fb.wake = nullptr;
       fb.cta_rowlist = e->d_lists + lb.off; fb.rows_cap = lb.rows_cap; fb.cpw = lb.ctas; fb.group0 = e->free_groups;
-      k_render_window<<<lb.ctas * nwin, SKB_CTA_THREADS, skb_free_smem_bytes(), st>>>(fb);
+      k_render_window<<<lb.ctas * nwin, SKB_CTA_THREADS, free_smem, st>>>(fb);
       e->stats.kernel_launches++;
       CK(cudaEventRecord(e->ev_b, st));
       if (groups_c > 0) {
         FreeArgs fc = fb;
         fc.cta_rowlist = e->d_lists + e->list_c.off; fc.rows_cap = e->list_c.rows_cap; fc.cpw = 0;
         fc.group0 = e->free_groups + groups_b;
-        k_render_biquad<<<e->list_c.ctas, SKB_CTA_THREADS, skb_free_smem_bytes(), st>>>(fc);
+        k_render_biquad<<<e->list_c.ctas, SKB_CTA_THREADS, free_smem, st>>>(fc);
         e->stats.kernel_launches++;
       }
       e->stats.wide_launches++;
@@ -1468,10 +1488,18 @@ static int batch_launch(skb_engine *e) {
     k_render_bins_warp<<<(e->n_small_bins + SKB_BINW_WARPS - 1) / SKB_BINW_WARPS, SKB_BINW_WARPS * 32, 0, st>>>(ba);
     e->stats.kernel_launches++;
   }
-  if ((int)e->bins.size() > e->n_small_bins) {                /* big components: one CTA each, one launch per callback, ops by k_apply_ops */
+  if ((int)e->bins.size() > e->n_big_end) {                   /* cyclic components above 1,024 voices: the slow, correct fallback */
+    k_render_bins_huge<<<(int)e->bins.size() - e->n_big_end, 1024, 0, st>>>(e->d_pq, e->d_sq[e->cur], e->cap, e->d_bins + e->n_big_end, e->d_tables,
+                                                         e->d_noise, nframes, (unsigned long long)e->batch.ssc0,
+                                                         e->d_partials, nframes, e->d_counters + 1,
+                                                         e->tap_on ? e->d_tap + (size_t)e->batch.tap_frame0 * e->n : nullptr, e->d_vos,
+                                                         e->tap_on ? e->n : 0, e->d_binx);
+    e->stats.kernel_launches++;
+  }
+  if (e->n_big_end > e->n_small_bins) {                       /* big components: one CTA each, one launch per callback, ops by k_apply_ops */
     const int nt = e->max_bin_threads;
     const size_t smem = (size_t)3 * nt * sizeof(float) + (size_t)2 * (nt / 32) * sizeof(float2);
-    k_render_bins<<<(int)e->bins.size() - e->n_small_bins, nt, smem, st>>>(e->d_pq, e->d_sq[e->cur], e->cap, e->d_bins + e->n_small_bins, e->d_tables,
+    k_render_bins<<<e->n_big_end - e->n_small_bins, nt, smem, st>>>(e->d_pq, e->d_sq[e->cur], e->cap, e->d_bins + e->n_small_bins, e->d_tables,
                                                          e->d_noise, nframes, (unsigned long long)e->batch.ssc0,
                                                          e->d_partials, nframes, e->d_counters + 1,
                                                          e->tap_on ? e->d_tap + (size_t)e->batch.tap_frame0 * e->n : nullptr, e->d_vos,

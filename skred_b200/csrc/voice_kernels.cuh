@@ -435,6 +435,79 @@ k_render_bins(const float4 *__restrict__ pq, float4 *__restrict__ sq, int cap,
   if (lane == 0 && na) atomicAdd(counter, (unsigned long long)na);
 }
 
+/* K2h  render_bins_huge: a CYCLIC modulation component of more than 1,024 voices (one shared feedback loop with thousands
+ * of readers).  Legal in the reference (any F / A / P / C graph is), rare, and inherently frame-lock-step — so this is the
+ * fallback that keeps it rendering instead of refusing it (round 1: SKB_ERR_CAPACITY): one CTA of 1,024 threads, a thread
+ * walks voices tid, tid + 1024, ... of the component per dependency level, every voice's record is re-read from and
+ * written back to HBM each frame, and voice_sample[] of the component is exchanged through a global buffer
+ * xs[3][cap] (previous frame, current frame, phase increments) under the same index rule as k_render_bins. */
+__global__ void __launch_bounds__(1024)
+k_render_bins_huge(const float4 *__restrict__ pq, float4 *sq, int cap,
+                   const skb_bin_desc *__restrict__ bins,
+                   const float *__restrict__ tables, const float *__restrict__ noise,
+                   int nframes, unsigned long long ssc_before,
+                   float2 *__restrict__ partials, int row_stride, unsigned long long *__restrict__ counter,
+                   float2 *__restrict__ tap, const int *__restrict__ voice_of_slot, int tap_n, float *xs) {
+  __shared__ float2 wsum[2][32];
+  const skb_bin_desc bd = bins[blockIdx.x];
+  const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  float *vs0 = xs + bd.slot0, *vs1 = xs + (size_t)cap + bd.slot0, *incs = xs + 2 * (size_t)cap + bd.slot0;
+  for (int i = tid; i < bd.size; i += nt) {
+    const float4 st0 = ldq(sq, 0, cap, bd.slot0 + i);
+    const float4 pa0 = ldq(pq, 0, cap, bd.slot0 + i);
+    vs0[i] = st0.z; vs1[i] = 0.0f; incs[i] = pa0.y;
+  }
+  float2 *out_row = partials + (size_t)bd.row * row_stride;
+  int na = 0;
+  __syncthreads();
+  for (int f = 0; f < nframes; f++) {
+    BinMods mod;
+    mod.prev = (f & 1) ? vs1 : vs0;
+    float *cur = (f & 1) ? vs0 : vs1;
+    mod.cur = cur;
+    mod.inc = incs;
+    float2 acc = make_float2(0.0f, 0.0f);
+    for (int lvl = 0; lvl < bd.nlevels; lvl++) {
+      for (int i = tid; i < bd.size; i += nt) {
+        const int slot = bd.slot0 + i;
+        if (__float_as_int(ldq(pq, 7, cap, slot).w) != lvl) continue;
+        VoiceP p; VoiceS s; VoiceK k;
+        load_params(pq, cap, slot, p);
+        load_state(sq, cap, slot, s);
+        derive_consts(p, k);
+        const float white = (p.flags & SKB_F_NOISE) ? __ldg(noise + f) : 0.0f;
+        const float2 o = voice_frame<true>(p, k, s, ssc_before + (unsigned long long)(f + 1), white, tables, mod);
+        cur[i] = s.sample;
+        store_state(sq, cap, slot, s);
+        na += s.nact;
+        if (tap_n) { const int tv = __ldg(voice_of_slot + slot); if (tv >= 0) tap[(size_t)f * tap_n + tv] = o; }
+        acc.x += o.x; acc.y += o.y;
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, d);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, d);
+    }
+    if (lane == 0) wsum[f & 1][warp] = acc;
+    if (f > 0 && tid == 0) {
+      float L = 0.0f, R = 0.0f;
+      for (int i = 0; i < nwarps; i++) { L += wsum[(f - 1) & 1][i].x; R += wsum[(f - 1) & 1][i].y; }
+      out_row[f - 1] = make_float2(L, R);
+    }
+  }
+  __syncthreads();
+  if (tid == 0 && nframes > 0) {
+    float L = 0.0f, R = 0.0f;
+    for (int i = 0; i < nwarps; i++) { L += wsum[(nframes - 1) & 1][i].x; R += wsum[(nframes - 1) & 1][i].y; }
+    out_row[nframes - 1] = make_float2(L, R);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) na += __shfl_xor_sync(0xffffffffu, na, d);
+  if (lane == 0 && na) atomicAdd(counter, (unsigned long long)na);
+}
+
 /* K2w  render_bins_warp: modulation groups of <= 32 voices, ONE WARP per bin.
  * The same frame-lock-step rule as k_render_bins (synth.c:526 loop order: modulator m < n is read at the current
  * frame, m > n at the previous one), but the voices of a bin are the lanes of one warp: the same-frame dependency

@@ -192,3 +192,25 @@ def recording_scenario(s, tmpdir):
     finally:
         os.chdir(cwd)
     return data
+
+
+def oversized_components(V=4096):
+    """Modulation components above the 1,024 voices one CTA holds (legal in the reference, used to be refused).
+    (a) CYCLIC: a feedback FM pair (voices 0 <-> 1) whose voice 0 also AM-modulates 1,500 carriers -> one component of 1,502
+        voices that has to stay frame-lock-step (k_render_bins_huge);
+    (b) ACYCLIC: one LFO (voice 2000) pan- and CZ-modulating 1,600 carriers -> levels (k_render_levels), no size limit."""
+    s = [("wave_set", 0, 0), ("freq_set", 0, 100.0), ("amp_set", 0, 1.0), ("freq_mod_set", 0, 1, 0.5),
+         ("wave_set", 1, 0), ("freq_set", 1, 150.0), ("amp_set", 1, 1.0), ("freq_mod_set", 1, 0, 0.5)]
+    for i in range(1500):
+        v = 2 + i
+        s += [("wave_set", v, i % 5), ("freq_set", v, 60.0 + 0.37 * i), ("amp_set", v, 0.02), ("amp_mod_set", v, 0, 0.5 + (i % 4) * 0.1),
+              ("pan_set", v, (i % 21 - 10) / 10.0)]
+        if i % 3 == 0:
+            s += [("filter_mode", v, 1), ("mmf_set_freq", v, 500.0 + 3.0 * i)]
+    s += [("wave_set", 2000, 0), ("freq_set", 2000, 1.5), ("amp_set", 2000, 1.0), ("wave_mute", 2000, 1)]
+    for i in range(1600):
+        v = 2001 + i
+        s += [("wave_set", v, 32 + i % 12), ("freq_set", v, 50.0 + 0.21 * i), ("amp_set", v, 0.02), ("pan_mod_set", v, 2000, 0.3),
+              ("cz_set", v, 1 + i % 5, 0.2 + 0.01 * (i % 30)), ("cmod_set", v, 2000, 0.2)]
+    ev = {3: [("amp_set", 0, 0.7), ("freq_set", 2000, 2.5), ("pan_set", 700, -0.5)]}
+    return _wl("oversized_components", s, events=ev, frames=6 * 512, voices=V)

@@ -476,3 +476,24 @@ def test_sequencer_patch_batched_equals_callbacks(n, golden_patches):
     assert maxdiff(oa, ob) <= 1e-6
     assert_state_equal(a.state(), b.state(), exact_keys=EXACT)
     assert lb < la, (la, lb)
+
+
+def test_oversized_modulation_components_vs_reference():
+    """Modulation components above 1,024 voices: a CYCLIC one of 1,502 voices (feedback pair + 1,500 AM readers:
+    k_render_bins_huge) and an ACYCLIC one of 1,601 voices (one LFO pan- and CZ-modulating 1,600 carriers: k_render_levels),
+    with events, against the compiled reference: every evolving word bit-exact, mix within 1e-5."""
+    from skred_b200 import workloads as W
+    V = 4096
+    if not O.have_ref(V):
+        pytest.skip("compiled reference for 4,096 voices not present")
+    wl = cases.oversized_components(V)
+    ref, gpu = O.RefSkred(V, run_seq=False), O.DropinCuda(V, run_seq=False)
+    outs = []
+    for s in (ref, gpu):
+        W.install(s, wl)
+        outs.append(s.render(wl["frames"], events=wl["events"]))
+    assert float(np.abs(outs[0]).max()) > 1e-3
+    assert maxdiff(outs[0], outs[1]) <= FULL_SCALE_TOL
+    assert_state_equal(ref.state(), gpu.state(), exact_keys=EXACT)
+    st = gpu.engine_stats()
+    assert st.n_group_voices >= 1502 + 1601
