@@ -511,10 +511,22 @@ def own_arm(a):
 
     # p50 host-observed latency of ONE 512-frame block through the same path (N > 1: every rank renders its shard of
     # the block, the exchange step, master volume + D2H on rank 0; timed on rank 0 between two host returns)
-    lat = None
+    lat, lat_parts = None, None
     if not a.no_latency:
         if world == 1:
+            tm2 = (C.c_double * 4)()
+            sk.lib.skb_shim_timing.argtypes = [C.c_void_p, C.c_int]
+            block_latency(sk, 50)
+            sk.lib.skb_shim_timing(tm2, 1)
+            s_l0 = sk.stats()
             lat = block_latency(sk, a.latency_blocks)
+            sk.lib.skb_shim_timing(tm2, 0)
+            s_l1 = sk.stats()
+            nb = float(a.latency_blocks)
+            eu = [(x - y) / nb * 1e-3 for x, y in zip(s_l1.host_us, s_l0.host_us)]
+            lat_parts = {"flush_and_traces": tm2[0] / nb * 1e3, "queue_segment": tm2[1] / nb * 1e3, "fire_events": tm2[2] / nb * 1e3,
+                         "finish": tm2[3] / nb * 1e3, "of_which_launch_host": eu[0], "finish_enqueue": eu[1], "stream_wait": eu[2],
+                         "device_ms_last_block": s_l1.last_render_ms, "note": "means over the blocks; the p50 is of the whole call"}
         else:
             blk = np.zeros((512, 2), dtype=np.float32)
             ts = []
@@ -570,7 +582,7 @@ def own_arm(a):
                                                                 "stream_wait": eng_us[2] * 1e-3}},
             "gpu_launches": launches + (a.steps if world > 1 else 0),
             "clocks": clk,
-            "block_latency_ms_p50": lat,
+            "block_latency_ms_p50": lat, "block_latency_parts_ms": lat_parts,
         }
         if world == 1 and not a.no_latency:
             line["block_latency_ms_p50_64_voices"] = block_latency_small(local, a.latency_blocks)
@@ -904,6 +916,19 @@ def modulation_leg(device):
     they run through k_render_levels (level_kernel.cuh)."""
     from skred_b200 import Skred
     out = {}
+    ef_old = os.environ.get("SKB_EARLY_FLUSH")
+    os.environ["SKB_EARLY_FLUSH"] = "0"       # one launch per synth() call: last_render_ms then covers the whole call
+    try:
+        return _modulation_leg(device, out)
+    finally:
+        if ef_old is None:
+            os.environ.pop("SKB_EARLY_FLUSH", None)
+        else:
+            os.environ["SKB_EARLY_FLUSH"] = ef_old
+
+
+def _modulation_leg(device, out):
+    from skred_b200 import Skred
     sk = Skred(64, device=device, private=True, max_frames=8192)
     sk.apply([("wave_reset", 0, 100), ("wave_set", 0, 0), ("freq_set", 0, 440.0), ("amp_set", 0, 4.0), ("freq_mod_set", 0, 1, 10.0),
               ("wave_set", 1, 0), ("freq_set", 1, 1.0), ("amp_set", 1, 50.0), ("wave_mute", 1, 1)])
@@ -930,7 +955,7 @@ def modulation_leg(device):
     except Exception as exc:
         out["configs0_0sk"]["reference_cpu_ms_per_callback_1_core"] = None
         sys.stderr.write("bench.py: 0.sk reference timing skipped: %r\n" % (exc,))
-    V, F = 1024, 4096      # 4,096 frames = one launch (the drop-in's early flush, SKB_EARLY_FLUSH): last_render_ms covers the call
+    V, F = 1024, 4096
     sk = Skred(V, device=device, private=True, max_frames=F)
     W.install(sk, W.config3(V, seconds=60.0, cmod_pairs=V // 2))
     buf = np.zeros((F, 2), dtype=np.float32)

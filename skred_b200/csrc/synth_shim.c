@@ -72,11 +72,13 @@ float volume_smoother_higher_smoothing = 0.3f;
 /* ======================================================================== */
 static skb_engine *g_engine = NULL;
 static int g_cfg_device = 0, g_cfg_rank = 0, g_cfg_world = 1, g_cfg_max_frames = 8192;
-static int g_early_flush_frames = 4096;   /* $SKB_EARLY_FLUSH: frames after which synth() launches what it has queued when at least
-                                             as many are still to come, so the GPU renders the first half of a long call while the
-                                             host fires and queues the events of the second (0 = one launch per chunk).  Measured:
-                                             synth(8192) 0.821 vs 0.848 ms; shorter halves lose (synth(4096) split at 2048: 0.529 vs
-                                             0.496 ms), a second launch costs ~45 us */
+static int g_early_flush_frames = 2048;   /* $SKB_EARLY_FLUSH: frames after which synth() launches what it has queued when at least
+                                             g_early_flush_rest are still to come, so the GPU renders the head of a long call while the
+                                             host fires and queues the events of the rest (0 = one launch per chunk).  Measured on
+                                             synth(8192), e2e ms per call: no split 0.848 (round 1), split at 4096 0.784, at 2048 0.768,
+                                             at 1024 0.768; a second launch costs ~45 us, so short calls are not split (round 1:
+                                             synth(4096) split at 2048 0.529 vs 0.496 ms) */
+static int g_early_flush_rest = 4096;     /* $SKB_EARLY_FLUSH_REST */
 static int g_scan_all = (VOICE_MAX <= 4096);
 
 static uint8_t g_dirty[VOICE_MAX];
@@ -133,6 +135,7 @@ static skb_engine *engine(void) {
   if ((s = getenv("SKB_NO_BATCH")) && atoi(s)) cfg.flags |= SKB_CFG_NO_BATCH;
   if ((s = getenv("SKB_WIDE")) && atoi(s)) cfg.flags |= SKB_CFG_WIDE;
   if ((s = getenv("SKB_EARLY_FLUSH"))) g_early_flush_frames = atoi(s);
+  if ((s = getenv("SKB_EARLY_FLUSH_REST"))) g_early_flush_rest = atoi(s);
   if ((s = getenv("SKB_NO_AFFINE")) && atoi(s)) cfg.flags |= SKB_CFG_NO_AFFINE;
   int r = skb_create(&g_engine, &cfg);
   if (r != SKB_OK || !g_engine) {
@@ -1255,7 +1258,7 @@ void synth(float *buffer, float *input, int num_frames, int num_channels, void *
       /* option: hand the GPU its first callbacks now, so that it renders them while the host fires and queues
        * the events of the rest (one deferred launch leaves it idle for ~95 us of host work per 4,096-frame
        * call); off by default, see g_early_flush_frames */
-      if (!early && g_early_flush_frames > 0 && done - chunk0 >= g_early_flush_frames && chunk1 - done >= g_early_flush_frames) {
+      if (!early && g_early_flush_frames > 0 && done - chunk0 >= g_early_flush_frames && chunk1 - done >= g_early_flush_rest) {
         if (skb_flush(g_engine) != SKB_OK) shim_die("skb_flush");
         early = 1;
       }

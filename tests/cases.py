@@ -198,7 +198,8 @@ def oversized_components(V=4096):
     """Modulation components above the 1,024 voices one CTA holds (legal in the reference, used to be refused).
     (a) CYCLIC: a feedback FM pair (voices 0 <-> 1) whose voice 0 also AM-modulates 1,500 carriers -> one component of 1,502
         voices that has to stay frame-lock-step (k_render_bins_huge);
-    (b) ACYCLIC: one LFO (voice 2000) pan- and CZ-modulating 1,600 carriers -> levels (k_render_levels), no size limit."""
+    (b) ACYCLIC: one LFO (voice 2000) pan- and CZ-modulating 1,600 carriers -> levels (k_render_levels), no size limit;
+    (c) CYCLIC, 100 voices: one CTA, frame-lock-step (k_render_bins)."""
     s = [("wave_set", 0, 0), ("freq_set", 0, 100.0), ("amp_set", 0, 1.0), ("freq_mod_set", 0, 1, 0.5),
          ("wave_set", 1, 0), ("freq_set", 1, 150.0), ("amp_set", 1, 1.0), ("freq_mod_set", 1, 0, 0.5)]
     for i in range(1500):
@@ -212,5 +213,12 @@ def oversized_components(V=4096):
         v = 2001 + i
         s += [("wave_set", v, 32 + i % 12), ("freq_set", v, 50.0 + 0.21 * i), ("amp_set", v, 0.02), ("pan_mod_set", v, 2000, 0.3),
               ("cz_set", v, 1 + i % 5, 0.2 + 0.01 * (i % 30)), ("cmod_set", v, 2000, 0.2)]
-    ev = {3: [("amp_set", 0, 0.7), ("freq_set", 2000, 2.5), ("pan_set", 700, -0.5)]}
+    # (c) a mid-size CYCLIC component: feedback pair 3700 <-> 3701 + 98 readers = 100 voices -> one CTA (k_render_bins)
+    s += [("wave_set", 3700, 0), ("freq_set", 3700, 80.0), ("amp_set", 3700, 1.0), ("freq_mod_set", 3700, 3701, 0.4),
+          ("wave_set", 3701, 1), ("freq_set", 3701, 120.0), ("amp_set", 3701, 1.0), ("amp_mod_set", 3701, 3700, 0.6)]
+    for i in range(98):
+        v = 3702 + i
+        s += [("wave_set", v, i % 5), ("freq_set", v, 90.0 + 1.3 * i), ("amp_set", v, 0.05), ("freq_mod_set", v, 3700 + i % 2, 1.0 + 0.1 * i),
+              ("pan_set", v, (i % 9 - 4) / 4.0)]
+    ev = {3: [("amp_set", 0, 0.7), ("freq_set", 2000, 2.5), ("pan_set", 700, -0.5), ("amp_set", 3701, 0.5)]}
     return _wl("oversized_components", s, events=ev, frames=6 * 512, voices=V)

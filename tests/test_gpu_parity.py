@@ -481,7 +481,8 @@ def test_sequencer_patch_batched_equals_callbacks(n, golden_patches):
 def test_oversized_modulation_components_vs_reference():
     """Modulation components above 1,024 voices: a CYCLIC one of 1,502 voices (feedback pair + 1,500 AM readers:
     k_render_bins_huge) and an ACYCLIC one of 1,601 voices (one LFO pan- and CZ-modulating 1,600 carriers: k_render_levels),
-    with events, against the compiled reference: every evolving word bit-exact, mix within 1e-5."""
+    plus a cyclic one of 100 voices (one CTA: k_render_bins), with events, against the compiled reference: every evolving word
+    bit-exact, mix within 1e-5."""
     from skred_b200 import workloads as W
     V = 4096
     if not O.have_ref(V):
@@ -496,4 +497,4 @@ def test_oversized_modulation_components_vs_reference():
     assert maxdiff(outs[0], outs[1]) <= FULL_SCALE_TOL
     assert_state_equal(ref.state(), gpu.state(), exact_keys=EXACT)
     st = gpu.engine_stats()
-    assert st.n_group_voices >= 1502 + 1601
+    assert st.n_group_voices >= 1502 + 1601 + 100

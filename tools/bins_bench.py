@@ -8,6 +8,7 @@ import sys
 
 import numpy as np
 
+os.environ["SKB_EARLY_FLUSH"] = "0"      # one launch per synth() call: last_render_ms then covers the whole call
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from skred_b200 import Skred, workloads as W  # noqa: E402
