@@ -249,13 +249,15 @@ def reference_arm(a):
     vps, sec, voices, procs, wall, frac = run_reference_cpu(V, frames, a.steps, a.warmup, cores, shard)
     line = {
         "impl": "reference", "metric": METRIC, "value": vps, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": (WORKLOAD % V) if a.gpus <= 1 else
-                   "%d x (%s), bounded sample: one %d-voice period of it (the own arm's N-GPU job repeats this load on every "
-                   "GPU; the reference's cost is linear in voices, its voice-samples/s does not depend on how many periods run)"
-                   % (a.gpus, WORKLOAD % V, V),
-                   "voices": voices, "frames_per_step": frames, "active_fraction": frac,
+        # the own arm's config at every N: ONE V-voice job (BASELINE configs[4]); each step of this arm is a bounded sample
+        # of one of its steps (the reference's cost is linear in frames: a rate measured on 2,048 frames is the rate of 8,192)
+        "config": {"workload": WORKLOAD % V, "voices": voices, "frames_per_step": a.frames, "block_frames": 512,
+                   "sample_frames_per_step": frames,
+                   "sample": "every step renders %d of the workload step's %d frames, all %d voices (ms_per_step is the sample's)"
+                             % (frames, a.frames, voices),
+                   "active_fraction": frac,
                    "counting": "rendered voice-frames only: voices skipped by synth.c:531-542 (finished one-shots) do not count",
                    "parallelism": "%d independent reference processes x %d voices (reference is single-threaded)" % (procs, shard)},
         "cpu_baseline": {"value": vps, "unit": UNIT, "cores": procs, "kind": "reference",
