@@ -80,7 +80,7 @@ __device__ __forceinline__ void rp_phase_block(RowSmem &S, int bi, int nf, const
         for (int k = 0; k < 8; k++) {
           const float q = phase + c.inc;                              /* :226 */
           const float w = q - c.hi_wrap;                              /* :247 (exact, see stage_phase) */
-          phase = (q >= c.hi_wrap) ? w : q;
+          phase = wrap_pick(q, w, c.hi_wrap);
           p8[k] = phase;
         }
 #pragma unroll
@@ -89,7 +89,7 @@ __device__ __forceinline__ void rp_phase_block(RowSmem &S, int bi, int nf, const
       for (; j < nf; j++) {
         const float q = phase + c.inc;
         const float w = q - c.hi_wrap;
-        phase = (q >= c.hi_wrap) ? w : q;
+        phase = wrap_pick(q, w, c.hi_wrap);
         ph[j][lane] = phase;
       }
       fs.phase = phase;
