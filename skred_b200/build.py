@@ -90,6 +90,19 @@ def build_engine_fast(force=False):
     return FAST_SO
 
 
+CANARY_SO = os.path.join(HERE, "variants", "canary", "libskred_b200.so")
+
+
+def build_engine_canary(force=False):
+    """The self-check build (-DSKB_CANARY=1, voice_kernels.cuh): the modulation-group kernels tag every exchanged voice_sample
+    with its frame and count reads that see another frame than the index rule promises (tests: test_exchange_canary)."""
+    srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "voice_kernels.cuh", "free_kernel.cuh", "row_kernel.cuh", "level_kernel.cuh", "partition.h")] + [
+        os.path.join(INC, "skred_b200.h"), __file__]
+    if not force and newer(CANARY_SO, srcs):
+        return CANARY_SO
+    return build_engine_variant("canary", ["-DSKB_CANARY=1"])
+
+
 def build_engine_variant(name, defines):
     """A tuning build of the engine (same soname) under skred_b200/variants/<name>/:
     select it with SKB_ENGINE_LIB=<path>.  defines: e.g. ["-DSKB_SUB=4", "-DSKB_CTA_WARPS=12"]."""
@@ -152,6 +165,7 @@ def build_shim(v, force=False):
 def build_all(voices=None, force=False, verbose=False):
     outs = [build_engine(force, verbose)]
     build_engine_fast(force)
+    build_engine_canary(force)
     for v in voices or DEFAULT_VOICES:
         outs.append(build_shim(v, force))
     return outs

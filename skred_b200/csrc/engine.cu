@@ -174,6 +174,8 @@ struct skb_engine {
 
 #if SKB_FAST_MODE
 const char *skb_backend_name(void) { return "cuda-sm100a-fast-nonparity"; }
+#elif SKB_CANARY
+const char *skb_backend_name(void) { return "cuda-sm100a-canary"; }      /* the exchange self-check build (voice_kernels.cuh) */
 #else
 const char *skb_backend_name(void) { return "cuda-sm100a"; }
 #endif
@@ -999,7 +1001,7 @@ static int replan(skb_engine *e, cudaStream_t st) {
     CK(cudaMemcpyAsync(e->d_bins, e->bins.data(), e->bins.size() * sizeof(skb_bin_desc), cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
     if ((int)e->bins.size() > e->n_big_end) {
-      cudaError_t rx = grow_dev(&e->d_binx, &e->binx_cap, (size_t)3 * e->cap);
+      cudaError_t rx = grow_dev(&e->d_binx, &e->binx_cap, (size_t)(SKB_CANARY ? 5 : 3) * e->cap);
       if (rx != cudaSuccess) return fail(e, SKB_ERR_CUDA, "huge-bin exchange alloc", cudaGetErrorString(rx));
     }
   }
@@ -1498,7 +1500,7 @@ static int batch_launch(skb_engine *e) {
   }
   if (e->n_big_end > e->n_small_bins) {                       /* big components: one CTA each, one launch per callback, ops by k_apply_ops */
     const int nt = e->max_bin_threads;
-    const size_t smem = (size_t)3 * nt * sizeof(float) + (size_t)2 * (nt / 32) * sizeof(float2);
+    const size_t smem = (size_t)3 * nt * sizeof(float) + (size_t)2 * (nt / 32) * sizeof(float2) + (SKB_CANARY ? (size_t)2 * nt * sizeof(int) : 0);
     k_render_bins<<<e->n_big_end - e->n_small_bins, nt, smem, st>>>(e->d_pq, e->d_sq[e->cur], e->cap, e->d_bins + e->n_small_bins, e->d_tables,
                                                          e->d_noise, nframes, (unsigned long long)e->batch.ssc0,
                                                          e->d_partials, nframes, e->d_counters + 1,

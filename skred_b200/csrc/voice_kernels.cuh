@@ -356,10 +356,27 @@ __device__ __forceinline__ void dev_apply_op(VoiceS &s, const skb_op &op) {
  * other with a CTA barrier in between. */
 struct skb_bin_desc { int slot0, size, nlevels, row; };
 
+/* SKB_CANARY=1 (skred_b200/variants/canary, tools/gpu_canary_check.py): every voice_sample[] word of the exchange carries the
+ * frame it was written in, and every modulator read checks that it sees the frame the index rule promises — the current
+ * frame for m < n, the previous one for m > n.  A missing or misplaced barrier (a reader ahead of its writer, a writer
+ * already one frame further) shows up as a count in skb_stats.wide_errors.  compute-sanitizer's racecheck is closed on
+ * the pool this was developed on; this is the in-kernel check instead. */
+#ifndef SKB_CANARY
+#define SKB_CANARY 0
+#endif
 struct BinMods {
   const float *prev, *cur, *inc;
+#if SKB_CANARY
+  const int *ptag, *ctag;
+  int frame;
+  unsigned long long *bad;
+#endif
   __device__ __forceinline__ float read(int ref) const {
     const int l = ref & SKB_REF_MASK;
+#if SKB_CANARY
+    const int tg = (ref & SKB_REF_CUR) ? ctag[l] : ptag[l];
+    if (tg != ((ref & SKB_REF_CUR) ? frame : frame - 1)) atomicAdd(bad, 1ull);
+#endif
     return (ref & SKB_REF_CUR) ? cur[l] : prev[l];
   }
   __device__ __forceinline__ float inc_of(int ref) const { return inc[ref & SKB_REF_MASK]; }
@@ -377,6 +394,10 @@ k_render_bins(const float4 *__restrict__ pq, float4 *__restrict__ sq, int cap,
   const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
   float *vs0 = bsm, *vs1 = bsm + nt, *incs = bsm + 2 * nt;
   float2 *wsum = (float2 *)(bsm + 3 * nt);        /* [2][nwarps] */
+#if SKB_CANARY
+  int *tg0 = (int *)(wsum + 2 * (nt >> 5)), *tg1 = tg0 + nt;
+  tg0[tid] = -1; tg1[tid] = -2;                   /* vs0 holds "the frame before the launch", vs1 nothing yet */
+#endif
   const bool live = tid < bd.size;
   const int slot = bd.slot0 + (live ? tid : 0);
   VoiceP p; VoiceS s; VoiceK k;
@@ -397,12 +418,19 @@ k_render_bins(const float4 *__restrict__ pq, float4 *__restrict__ sq, int cap,
     float *cur = (f & 1) ? vs0 : vs1;
     mod.cur = cur;
     mod.inc = incs;
+#if SKB_CANARY
+    int *ctagw = (f & 1) ? tg0 : tg1;
+    mod.ptag = (f & 1) ? tg1 : tg0; mod.ctag = ctagw; mod.frame = f; mod.bad = counter + 18;
+#endif
     const float white = wants_noise ? __ldg(noise + f) : 0.0f;
     float2 o = make_float2(0.0f, 0.0f);
     for (int lvl = 0; lvl < bd.nlevels; lvl++) {
       if (live && p.level == lvl) {
         o = voice_frame<true>(p, k, s, ssc_before + (unsigned long long)(f + 1), white, tables, mod);
         cur[tid] = s.sample;
+#if SKB_CANARY
+        ctagw[tid] = f;
+#endif
       }
       __syncthreads();
     }
@@ -452,10 +480,16 @@ k_render_bins_huge(const float4 *__restrict__ pq, float4 *sq, int cap,
   const skb_bin_desc bd = bins[blockIdx.x];
   const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
   float *vs0 = xs + bd.slot0, *vs1 = xs + (size_t)cap + bd.slot0, *incs = xs + 2 * (size_t)cap + bd.slot0;
+#if SKB_CANARY
+  int *tg0 = (int *)(xs + 3 * (size_t)cap) + bd.slot0, *tg1 = tg0 + cap;
+#endif
   for (int i = tid; i < bd.size; i += nt) {
     const float4 st0 = ldq(sq, 0, cap, bd.slot0 + i);
     const float4 pa0 = ldq(pq, 0, cap, bd.slot0 + i);
     vs0[i] = st0.z; vs1[i] = 0.0f; incs[i] = pa0.y;
+#if SKB_CANARY
+    tg0[i] = -1; tg1[i] = -2;
+#endif
   }
   float2 *out_row = partials + (size_t)bd.row * row_stride;
   int na = 0;
@@ -466,6 +500,10 @@ k_render_bins_huge(const float4 *__restrict__ pq, float4 *sq, int cap,
     float *cur = (f & 1) ? vs0 : vs1;
     mod.cur = cur;
     mod.inc = incs;
+#if SKB_CANARY
+    int *ctagw = (f & 1) ? tg0 : tg1;
+    mod.ptag = (f & 1) ? tg1 : tg0; mod.ctag = ctagw; mod.frame = f; mod.bad = counter + 18;
+#endif
     float2 acc = make_float2(0.0f, 0.0f);
     for (int lvl = 0; lvl < bd.nlevels; lvl++) {
       for (int i = tid; i < bd.size; i += nt) {
@@ -478,6 +516,9 @@ k_render_bins_huge(const float4 *__restrict__ pq, float4 *sq, int cap,
         const float white = (p.flags & SKB_F_NOISE) ? __ldg(noise + f) : 0.0f;
         const float2 o = voice_frame<true>(p, k, s, ssc_before + (unsigned long long)(f + 1), white, tables, mod);
         cur[i] = s.sample;
+#if SKB_CANARY
+        ctagw[i] = f;
+#endif
         store_state(sq, cap, slot, s);
         na += s.nact;
         if (tap_n) { const int tv = __ldg(voice_of_slot + slot); if (tv >= 0) tap[(size_t)f * tap_n + tv] = o; }
@@ -535,6 +576,9 @@ __global__ void __launch_bounds__(SKB_BINW_WARPS * 32) k_render_bins_warp(const 
   __shared__ float s_inc[SKB_BINW_WARPS][32];
   __shared__ float2 s_tile[SKB_BINW_WARPS][SKB_TILE_FLOAT2];
   __shared__ float2 s_row[SKB_BINW_WARPS][SKB_UNIT];
+#if SKB_CANARY
+  __shared__ int s_tag[SKB_BINW_WARPS][2][32];
+#endif
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x * SKB_BINW_WARPS + warp;
   if (b >= a.nbins) return;                                   /* (warps are independent: no CTA barrier below) */
@@ -551,6 +595,10 @@ __global__ void __launch_bounds__(SKB_BINW_WARPS * 32) k_render_bins_warp(const 
   float2 *mytile = s_tile[warp], *myrow = s_row[warp];
   vs0[lane] = live ? s.sample : 0.0f;
   vs1[lane] = 0.0f;
+#if SKB_CANARY
+  int *tg0 = s_tag[warp][0], *tg1 = s_tag[warp][1];
+  tg0[lane] = -1; tg1[lane] = -2;
+#endif
   s_inc[warp][lane] = live ? p.inc : 0.0f;
   const bool wants_noise = live && (p.flags & SKB_F_NOISE);
   float2 *out_row = a.partials + (size_t)bd.row * a.row_stride;
@@ -572,6 +620,9 @@ __global__ void __launch_bounds__(SKB_BINW_WARPS * 32) k_render_bins_warp(const 
           dev_apply_op(s, op);
         }
         ((fr & 1) ? vs1 : vs0)[lane] = s.sample;              /* what modulators read as "previous frame" (voice_reset clears it) */
+#if SKB_CANARY
+        ((fr & 1) ? tg1 : tg0)[lane] = fr - 1;
+#endif
       }
       __syncwarp();
     }
@@ -584,12 +635,19 @@ __global__ void __launch_bounds__(SKB_BINW_WARPS * 32) k_render_bins_warp(const 
         float *cur = (fr & 1) ? vs0 : vs1;
         mod.cur = cur;
         mod.inc = s_inc[warp];
+#if SKB_CANARY
+        int *ctagw = (fr & 1) ? tg0 : tg1;
+        mod.ptag = (fr & 1) ? tg1 : tg0; mod.ctag = ctagw; mod.frame = fr; mod.bad = a.counter + 18;
+#endif
         const float white = wants_noise ? __ldg(a.noise + fr) : 0.0f;
         float2 o = make_float2(0.0f, 0.0f);
         for (int lvl = 0; lvl < bd.nlevels; lvl++) {
           if (live && p.level == lvl) {
             o = voice_frame<true>(p, k, s, a.ssc_before + (unsigned long long)(fr + 1), white, a.tables, mod);
             cur[lane] = s.sample;
+#if SKB_CANARY
+            ctagw[lane] = fr;
+#endif
           }
           __syncwarp();
         }

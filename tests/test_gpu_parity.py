@@ -498,3 +498,23 @@ def test_oversized_modulation_components_vs_reference():
     assert_state_equal(ref.state(), gpu.state(), exact_keys=EXACT)
     st = gpu.engine_stats()
     assert st.n_group_voices >= 1502 + 1601 + 100
+
+
+def test_exchange_canary(tmp_path):
+    """compute-sanitizer's racecheck is closed on the GPU pool this was developed on (it refuses to start), so the
+    shared-memory / global exchange of the frame-lock-step modulation kernels (k_render_bins_warp, k_render_bins,
+    k_render_bins_huge) is checked in-kernel instead: the engine built -DSKB_CANARY=1 tags every exchanged voice_sample[]
+    with the frame it was written in and counts modulator reads that see another frame than synth.c:526's loop order
+    promises.  tools/gpu_canary_check.py renders the `mods` set (with and without the per-voice tap) and the oversized
+    components against the reference with that build: parity as usual, canary count 0."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "skred_b200", "variants", "canary", "libskred_b200.so")
+    if not os.path.exists(lib):
+        pytest.skip("canary build missing: python -m skred_b200.build")
+    out = os.path.join(root, "gpurun_out", "exchange_canary.txt") if os.path.isdir(os.path.join(root, "gpurun_out")) else str(tmp_path / "canary.txt")
+    env = dict(os.environ, SKB_ENGINE_LIB=lib)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_canary_check.py"), out], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "canary mismatches 0" in r.stdout and "FAIL" not in r.stdout, r.stdout
