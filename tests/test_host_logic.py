@@ -284,3 +284,44 @@ def test_bench_l2_flushed_headline():
     assert out["config"]["value_l2_unflushed"] == 5.5e11 and out["config"]["ms_per_step_l2_unflushed"] == 0.70
     assert "value_l2_flushed" not in out["config"] and out["config"]["l2"].startswith("flushed before every timed step")
     assert abs(out["config"]["active_fraction"] - 0.725) < 1e-12
+
+
+def test_partition_stable_keeps_owners_and_moves_the_smaller_side(tmp_path):
+    """csrc/partition.h: skb_partition_stable.  Ownership survives re-plans: an unchanged component stays, a
+    component that merged voices of several shards goes to the shard that held most of them (ties -> lowest rank), a
+    component that split leaves its voices where they were.  Compiled here from the header (plain C, shared with the engine)."""
+    import subprocess
+    src = tmp_path / "pstable.c"
+    src.write_text('#include "partition.h"\n'
+                   'void t_first(const int32_t *comp, int n, int world, int32_t *owner) { skb_partition(comp, n, world, owner); }\n'
+                   'void t_stable(const int32_t *comp, int n, int world, const int32_t *prev, int32_t *owner) '
+                   '{ skb_partition_stable(comp, n, world, prev, owner); }\n')
+    so = tmp_path / "pstable.so"
+    subprocess.run(["gcc", "-O1", "-shared", "-fPIC", "-I" + os.path.join(ROOT, "skred_b200", "csrc"), "-I" + os.path.join(ROOT, "include"),
+                    str(src), "-o", str(so)], check=True)
+    lib = C.CDLL(str(so))
+    n, world = 12, 3
+    I32 = C.c_int32 * n
+
+    def first(comp):
+        o = I32()
+        lib.t_first(I32(*comp), n, world, o)
+        return list(o)
+
+    def stable(comp, prev):
+        o = I32()
+        lib.t_stable(I32(*comp), n, world, I32(*prev), o)
+        return list(o)
+
+    solo = list(range(n))
+    own0 = first(solo)
+    assert own0 == [v % 3 for v in range(n)]                       # least-loaded dealing, ties to the lowest rank
+    assert stable(solo, own0) == own0                              # nothing changed: nobody moves
+    merged = [0, 0, 0, 0] + list(range(4, n))                      # voices 0..3 become one component: owners were 0,1,2,0
+    own1 = stable(merged, own0)
+    assert own1[:4] == [0, 0, 0, 0] and own1[4:] == own0[4:]       # rank 0 held two of them: the other two move, nobody else does
+    tie = [0, 0] + list(range(2, n))                               # voices 0,1 (owners 0 and 1): tie -> lowest rank
+    assert stable(tie, own0)[:2] == [0, 0]
+    own2 = stable(solo, own1)                                      # the component splits again: its voices stay where they are
+    assert own2 == own1
+    assert first(merged)[:4] == [0, 0, 0, 0]
