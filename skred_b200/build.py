@@ -163,9 +163,15 @@ def build_shim(v, force=False):
 
 
 def build_all(voices=None, force=False, verbose=False):
-    outs = [build_engine(force, verbose)]
-    build_engine_fast(force)
-    build_engine_canary(force)
+    # the three engine builds (parity, non-parity fast, exchange canary) are independent nvcc runs of ~1.5 min each: side by side
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=3) as pool:
+        f_main = pool.submit(build_engine, force, verbose)
+        f_fast = pool.submit(build_engine_fast, force)
+        f_can = pool.submit(build_engine_canary, force)
+        outs = [f_main.result()]
+        f_fast.result()
+        f_can.result()
     for v in voices or DEFAULT_VOICES:
         outs.append(build_shim(v, force))
     return outs

@@ -1026,7 +1026,12 @@ static int replan(skb_engine *e, cudaStream_t st) {
   e->need_plan = false;
   e->stats.replans++;
   e->stats.n_free_voices = e->n_free;
-  e->stats.n_group_voices = e->n_slots - e->n_free_pad;
+  {
+    /* voices rendered by the modulation kernels (levelled rows are padded to 32 per level: count voices, not slots) */
+    int ng = 0;
+    for (int sl = e->n_free_pad; sl < e->n_slots; sl++) ng += e->voice_of_slot[(size_t)sl] >= 0;
+    e->stats.n_group_voices = ng;
+  }
   e->stats.n_groups = (int)e->bins.size();
   e->stats.n_owned_voices = e->n_free + e->stats.n_group_voices;
   return SKB_OK;
