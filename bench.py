@@ -105,7 +105,7 @@ def kernel_source_hash():
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "skred_b200", "csrc")
-    for f in ("engine.cu", "voice_kernels.cuh", "free_kernel.cuh", "row_kernel.cuh", "level_kernel.cuh", "partition.h"):
+    for f in ("engine.cu", "free_lo.cu", "voice_kernels.cuh", "free_kernel.cuh", "row_kernel.cuh", "level_kernel.cuh", "partition.h"):
         with open(os.path.join(d, f), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()[:16]

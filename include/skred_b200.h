@@ -318,6 +318,7 @@ typedef struct skb_stats {
                                  [2] waiting for the stream in skb_finish, [3] unused */
   uint64_t rows_launches;     /* launches rendered by k_render_rows */
   uint64_t migrated_voices;   /* voices whose state moved to another GPU at a re-plan (a modulation edge joined two shards) */
+  uint64_t lo_launches;       /* launches of the few-voices build of k_render_free (csrc/free_lo.cu) */
   uint64_t h2d_bytes, d2h_bytes; /* bytes the render path copied host -> device (parameter records, ops, per-launch staging
                                     block, noise and gain traces) and device -> host (stereo block, counters, tap) */
 } skb_stats;

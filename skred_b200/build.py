@@ -61,11 +61,11 @@ def shim_so(v):
 
 
 def build_engine(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "voice_kernels.cuh", "free_kernel.cuh", "row_kernel.cuh", "level_kernel.cuh", "partition.h")] + [
+    srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "free_lo.cu", "voice_kernels.cuh", "free_kernel.cuh", "row_kernel.cuh", "level_kernel.cuh", "partition.h")] + [
         os.path.join(INC, "skred_b200.h"), __file__]
     if not force and newer(ENGINE_SO, srcs):
         return ENGINE_SO
-    out = run([NVCC] + NVCC_FLAGS + ["-I" + INC, "-I" + CSRC, srcs[0], "-o", ENGINE_SO])
+    out = run([NVCC] + NVCC_FLAGS + ["-I" + INC, "-I" + CSRC, srcs[0], srcs[1], "-o", ENGINE_SO])
     log = os.path.join(ROOT, "build", "ptxas_engine.log")
     os.makedirs(os.path.dirname(log), exist_ok=True)
     open(log, "w").write(out)
@@ -80,13 +80,13 @@ FAST_SO = os.path.join(HERE, "fast", "libskred_b200.so")
 def build_engine_fast(force=False):
     """The NON-PARITY build: FMA contraction on, interpolating oscillator read.  Same soname, its own
     directory; selected with SKB_ENGINE_LIB (bench.py's fast_mode leg).  No parity test ever loads it."""
-    srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "voice_kernels.cuh", "free_kernel.cuh", "row_kernel.cuh", "level_kernel.cuh", "partition.h")] + [
+    srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "free_lo.cu", "voice_kernels.cuh", "free_kernel.cuh", "row_kernel.cuh", "level_kernel.cuh", "partition.h")] + [
         os.path.join(INC, "skred_b200.h"), __file__]
     if not force and newer(FAST_SO, srcs):
         return FAST_SO
     os.makedirs(os.path.dirname(FAST_SO), exist_ok=True)
     flags = [f for f in NVCC_FLAGS if f != "-fmad=false"] + ["-fmad=true", "-DSKB_FAST_MODE=1"]
-    run([NVCC] + flags + ["-I" + INC, "-I" + CSRC, os.path.join(CSRC, "engine.cu"), "-o", FAST_SO])
+    run([NVCC] + flags + ["-I" + INC, "-I" + CSRC, os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "free_lo.cu"), "-o", FAST_SO])
     return FAST_SO
 
 
@@ -96,7 +96,7 @@ CANARY_SO = os.path.join(HERE, "variants", "canary", "libskred_b200.so")
 def build_engine_canary(force=False):
     """The self-check build (-DSKB_CANARY=1, voice_kernels.cuh): the modulation-group kernels tag every exchanged voice_sample
     with its frame and count reads that see another frame than the index rule promises (tests: test_exchange_canary)."""
-    srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "voice_kernels.cuh", "free_kernel.cuh", "row_kernel.cuh", "level_kernel.cuh", "partition.h")] + [
+    srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "free_lo.cu", "voice_kernels.cuh", "free_kernel.cuh", "row_kernel.cuh", "level_kernel.cuh", "partition.h")] + [
         os.path.join(INC, "skred_b200.h"), __file__]
     if not force and newer(CANARY_SO, srcs):
         return CANARY_SO
@@ -109,7 +109,7 @@ def build_engine_variant(name, defines):
     d = os.path.join(HERE, "variants", name)
     os.makedirs(d, exist_ok=True)
     out = os.path.join(d, "libskred_b200.so")
-    run([NVCC] + NVCC_FLAGS + list(defines) + ["-I" + INC, "-I" + CSRC, os.path.join(CSRC, "engine.cu"), "-o", out])
+    run([NVCC] + NVCC_FLAGS + list(defines) + ["-I" + INC, "-I" + CSRC, os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "free_lo.cu"), "-o", out])
     return out
 
 

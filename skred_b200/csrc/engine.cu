@@ -77,6 +77,10 @@ struct skb_engine {
   float *d_binx = nullptr; size_t binx_cap = 0;      /* voice_sample exchange of the huge bins: [3][cap] floats */
   /* How many envelopes are in a transient, roughly: envelope triggers / releases seen, halved every 0.5 s of audio.  Only
    * picks the shared-memory size of the free-voice kernels (free_kernel.cuh: SKB_ENV_WARP_FLOATS_*), never a result. */
+  /* few rows per SM: the launch lasts as long as its slowest lone warp, and free_lo.cu's build of the kernel (more
+   * registers and frames per pipeline stage, fewer warps) runs a lone warp ~17 % faster.  lo_ok = the current plan gives
+   * no CTA more rows than that kernel has warps; lo_mode: $SKB_LO (0 never, 1 when lo_ok [default]). */
+  bool lo_ok = false; int lo_mode = 1; uint64_t lo_launches = 0;
   double env_activity = 0.0; long env_ops_pending = 0;
   int env_floats_forced = 0;         /* $SKB_ENV_FLOATS: testing aid */
   int rows_cap = 0;                  /* entries per CTA in d_ctarows */
@@ -171,6 +175,13 @@ struct skb_engine {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_stage_copied[2] = {nullptr, nullptr}, ev_stage_done[2] = {nullptr, nullptr};
 };
+
+/* free_lo.cu: k_render_free compiled for few voices per GPU (8 frames per pipeline stage, 8 warps per CTA) */
+extern "C" size_t skb_lo_free_args_bytes(void);
+extern "C" size_t skb_lo_free_smem_bytes(int env_warp_floats);
+extern "C" int skb_lo_free_rows_per_cta(void);
+extern "C" int skb_lo_free_init(void);
+extern "C" void skb_lo_free_launch(const void *args, int ctas, size_t smem, void *stream);
 
 #if SKB_FAST_MODE
 const char *skb_backend_name(void) { return "cuda-sm100a-fast-nonparity"; }
@@ -293,6 +304,7 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
    * launch of 8,192 voices, slower from 16,384 voices up — not enough to switch by default: opt-in */
   e->rows_mode = (cfg->flags & SKB_CFG_ROWS) ? 1 : 0;
   e->rows_auto_max = 2 * e->n_sm;
+  { const char *s = getenv("SKB_LO"); if (s && s[0]) e->lo_mode = atoi(s); }
   { const char *s = getenv("SKB_ENV_FLOATS"); if (s && s[0]) { const int v = atoi(s); if (v >= SKB_ENV_WARP_FLOATS_SMALL && v <= SKB_ENV_WARP_FLOATS_LARGE) e->env_floats_forced = v & ~3; } }
   { const char *s = getenv("SKB_ROWS"); if (s && s[0]) e->rows_mode = atoi(s);
     s = getenv("SKB_ROWS_MAX"); if (s && s[0]) e->rows_auto_max = atoi(s); }
@@ -342,6 +354,7 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
                                  (int)skb_free_smem_bytes(SKB_ENV_WARP_FLOATS_LARGE)) == cudaSuccess &&
             cudaFuncSetAttribute(k_render_biquad, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)skb_free_smem_bytes(SKB_ENV_WARP_FLOATS_LARGE)) == cudaSuccess &&
+            skb_lo_free_init() == 0 && skb_lo_free_args_bytes() == sizeof(FreeArgs) &&
             cudaFuncSetAttribute(k_render_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)skb_rows_smem_bytes()) == cudaSuccess &&
             cudaFuncSetAttribute(k_render_levels, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -880,6 +893,16 @@ static int replan(skb_engine *e, cudaStream_t st) {
     };
     invert(ctarows, e->free_ctas, e->rows_cap, e->cta_of_row);
     e->free_groups = e->free_ctas * (e->rows_cap / SKB_CTA_WARPS);
+    {
+      /* free_lo.cu's kernel takes the first skb_lo_free_rows_per_cta() entries of a CTA's list in ONE pass: usable when the
+       * lists are one batch long and nothing lies beyond those entries (a GPU with few voices) */
+      const int lo_rows = skb_lo_free_rows_per_cta();
+      bool ok = nrows > 0 && e->rows_cap == SKB_CTA_WARPS;
+      for (int c = 0; ok && c < e->free_ctas; c++)
+        for (int k = lo_rows; k < e->rows_cap; k++)
+          if (ctarows[(size_t)c * e->rows_cap + k] >= 0) { ok = false; break; }
+      e->lo_ok = ok;
+    }
     /* pass A of a time-split launch: the same rows, the wide ones flagged and costed as the light body */
     auto append = [&lists](const std::vector<int> &l, int ctas, int rcap) {
       skb_engine::RowList rl; rl.off = (int)lists.size(); rl.ctas = ctas; rl.rows_cap = rcap;
@@ -1463,6 +1486,7 @@ static int batch_launch(skb_engine *e) {
       k_render_rows<<<e->n_free_rows, RP_THREADS, skb_rows_smem_bytes(), st>>>(fa);
       e->stats.rows_launches++;
     } else if (e->tap_on) k_render_free_tap<<<e->free_ctas, SKB_CTA_THREADS, free_smem, st>>>(fa);
+    else if (e->lo_ok && e->lo_mode) { skb_lo_free_launch(&fa, e->free_ctas, skb_lo_free_smem_bytes(fa.env_warp_floats), st); e->lo_launches++; e->stats.lo_launches++; }
     else k_render_free<<<e->free_ctas, SKB_CTA_THREADS, free_smem, st>>>(fa);
     e->stats.kernel_launches++;
     if (wide) {

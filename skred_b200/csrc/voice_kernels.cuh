@@ -341,6 +341,7 @@ __device__ __forceinline__ void dev_apply_op(VoiceS &s, const skb_op &op) {
 
 /* K1  render_free: free_kernel.cuh; K1b render_rows (few voices per GPU): row_kernel.cuh */
 #include "free_kernel.cuh"
+#ifndef SKB_LO_VARIANT        /* (free_lo.cu compiles k_render_free a second time with other tuning constants: nothing below) */
 #include "row_kernel.cuh"
 #include "level_kernel.cuh"
 
@@ -839,3 +840,4 @@ __global__ void k_scatter_state(float4 *__restrict__ sq, int cap, const int *__r
   s.panL = o.pan_left; s.panR = o.pan_right; s.env_start = o.env_start; s.env_rel = o.env_release; s.aux = 0;
   store_state(sq, cap, slot, s);
 }
+#endif /* !SKB_LO_VARIANT */

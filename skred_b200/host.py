@@ -86,7 +86,7 @@ class skb_stats(C.Structure):
                 ("phase_cycles", C.c_uint64 * 8), ("cta_batches", C.c_uint64),
                 ("wide_launches", C.c_uint64), ("wide_errors", C.c_uint64), ("last_wide_ms", C.c_float * 3),
                 ("_pad2", C.c_int32), ("host_us", C.c_double * 4),
-                ("rows_launches", C.c_uint64), ("migrated_voices", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("rows_launches", C.c_uint64), ("migrated_voices", C.c_uint64), ("lo_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
 class SynthAPI:
