@@ -6,7 +6,8 @@ import re
 import subprocess
 import sys
 
-so = "skred_b200/libskred_b200.so"
+import os
+so = os.environ.get("SKB_SO", "skred_b200/libskred_b200.so")
 fn = sys.argv[1] if len(sys.argv) > 1 else "k_render_free"
 mn = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 mx = int(sys.argv[3]) if len(sys.argv) > 3 else 700
