@@ -440,7 +440,7 @@ def own_arm(a):
 
     # dominant kernel alone (k_render_free + bins + reduce), CUDA events inside the engine
     kern_ms, kern_active = [], []
-    for _ in range(3):
+    for _ in range(15):                                   # (the median of 15 isolated launches: 3 were too few for a stable frac)
         a_b = sk.stats().active_voice_frames
         step_device()
         sk.lib.skb_shim_discard_gain()
@@ -504,8 +504,8 @@ def own_arm(a):
     act_e2e = sum_over_ranks(s_a.active_voice_frames - s_b.active_voice_frames)
     value = act_dev / (dev_ms * 1e-3)
     e2e = act_e2e / e2e_s
-    k_ms = float(np.mean(kern_ms))
-    k_act = float(np.mean(kern_active))
+    k_ms = float(np.median(kern_ms))
+    k_act = float(np.median(kern_active))
     ncu = load_ncu_counters()
     if ncu and (ncu.get("frames") != F or ncu.get("voices_on_gpu") != owned):
         ncu = None                                        # counters of another launch shape

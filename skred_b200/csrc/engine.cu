@@ -17,6 +17,7 @@
  * Reference mapping: synth() synth.c:502-630; see DESIGN.md.
  */
 #include <cuda_runtime.h>
+#include <atomic>
 #include <dlfcn.h>
 #include <nccl.h>
 #include <stdint.h>
@@ -134,6 +135,13 @@ struct skb_engine {
 
   /* pinned staging */
   float *h_gain = nullptr, *h_noise = nullptr, *h_out = nullptr;
+  /* skb_finish without copies: k_finish_host writes the frames and the counters into mapped host memory and raises h_flag
+   * (SKB_FINISH_COPY=1 selects the staged path: k_finish -> d_out -> two device-to-host copies -> stream synchronise) */
+  volatile unsigned int *h_flag = nullptr;
+  unsigned int *d_fin_ticket = nullptr;
+  unsigned int fin_seq = 0;
+  bool finish_direct = false;
+  float2 *dv_out = nullptr; unsigned long long *dv_counters = nullptr; unsigned int *dv_flag = nullptr;   /* device views */
   int *h_idx = nullptr; size_t h_idx_cap = 0;
   float4 *h_recs = nullptr; size_t h_recs_cap = 0;
   skb_op *h_ops = nullptr; size_t h_ops_cap = 0;
@@ -366,6 +374,25 @@ int skb_create(skb_engine **out, const skb_config *cfg) {
             cudaMemset(e->d_sq[0], 0, (size_t)SKB_NSQ * e->cap * sizeof(float4)) == cudaSuccess &&
             cudaMemset(e->d_sq[1], 0, (size_t)SKB_NSQ * e->cap * sizeof(float4)) == cudaSuccess;
   if (ok) {
+    /* direct finish: needs the pinned buffers in the device's address space (UVA: they are) */
+    const char *fc = getenv("SKB_FINISH_COPY");
+    unsigned int *hf = nullptr;
+    if (!(fc && atoi(fc) != 0) &&
+        cudaHostAlloc((void **)&hf, 64, cudaHostAllocMapped) == cudaSuccess &&
+        cudaMalloc((void **)&e->d_fin_ticket, sizeof(unsigned int)) == cudaSuccess &&
+        cudaMemset(e->d_fin_ticket, 0, sizeof(unsigned int)) == cudaSuccess &&
+        cudaHostGetDevicePointer((void **)&e->dv_out, e->h_out, 0) == cudaSuccess &&
+        cudaHostGetDevicePointer((void **)&e->dv_counters, e->h_counters, 0) == cudaSuccess &&
+        cudaHostGetDevicePointer((void **)&e->dv_flag, hf, 0) == cudaSuccess) {
+      *hf = 0u;
+      e->h_flag = hf;
+      e->finish_direct = true;
+    } else {
+      cudaGetLastError();
+      if (hf) cudaFreeHost(hf);
+    }
+  }
+  if (ok) {
     /* the bin kernel may need more than 48 KB? no: 3*nt floats + 2*nwarps float2 <= 12.8 KB */
     e->tables_cap = (size_t)4 << 20;
     ok = cudaMalloc((void **)&e->d_tables, e->tables_cap * sizeof(float)) == cudaSuccess;
@@ -404,6 +431,8 @@ void skb_destroy(skb_engine *e) {
   if (e->ev_b) cudaEventDestroy(e->ev_b);
   cudaFree(e->d_part2); cudaFree(e->d_tickets); cudaFree(e->d_counters);
   cudaFreeHost(e->h_counters);
+  if (e->h_flag) cudaFreeHost((void *)e->h_flag);
+  cudaFree(e->d_fin_ticket);
   cudaFreeHost(e->h_gain); cudaFreeHost(e->h_noise); cudaFreeHost(e->h_out); cudaFreeHost(e->h_idx);
   cudaFreeHost(e->h_recs); cudaFreeHost(e->h_ops); cudaFreeHost(e->h_runs); cudaFreeHost(e->h_snap);
   if (e->ev_h2d) cudaEventDestroy(e->ev_h2d);
@@ -1663,18 +1692,50 @@ int skb_finish(skb_engine *e, const float *d_mix, int nframes, const float *gain
   const double t_f0 = host_now_us();
   if (use_stream(e, st)) return e->err;
   if (wait_staging(e)) return e->err;
-  memcpy(e->h_gain, gain, (size_t)nframes * sizeof(float));
-  CK(cudaMemcpyAsync(e->d_gain, e->h_gain, (size_t)nframes * sizeof(float), cudaMemcpyHostToDevice, st));
-  e->stats.h2d_bytes += (uint64_t)((size_t)nframes * sizeof(float));
-  CK(cudaEventRecord(e->ev_h2d, st));
-  k_finish<<<(nframes + 255) / 256, 256, 0, st>>>((const float2 *)d_mix, e->d_gain, e->d_out, nframes);
-  e->stats.kernel_launches++;
-  CK(cudaMemcpyAsync(e->h_out, e->d_out, (size_t)nframes * sizeof(float2), cudaMemcpyDeviceToHost, st));
-  e->stats.d2h_bytes += (uint64_t)nframes * sizeof(float2) + SKB_N_COUNTERS * sizeof(unsigned long long);
-  CK(cudaMemcpyAsync(e->h_counters, e->d_counters, SKB_N_COUNTERS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-  const double t_f1 = host_now_us();
-  CK(cudaStreamSynchronize(st));
-  const double t_f2 = host_now_us();
+  /* the master-volume trace: one value when the one-pole sits on its fixed point (the usual case) */
+  bool gain_flat = true;
+  for (int i = 1; i < nframes && gain_flat; i++) gain_flat = gain[i] == gain[0];
+  if (!(e->finish_direct && gain_flat)) {
+    memcpy(e->h_gain, gain, (size_t)nframes * sizeof(float));
+    CK(cudaMemcpyAsync(e->d_gain, e->h_gain, (size_t)nframes * sizeof(float), cudaMemcpyHostToDevice, st));
+    e->stats.h2d_bytes += (uint64_t)((size_t)nframes * sizeof(float));
+    CK(cudaEventRecord(e->ev_h2d, st));
+  }
+  double t_f1, t_f2;
+  if (e->finish_direct) {
+    const unsigned int seq = ++e->fin_seq ? e->fin_seq : ++e->fin_seq;       /* (never 0: the flag's idle value) */
+    k_finish_host<<<(nframes + 255) / 256, 256, 0, st>>>((const float2 *)d_mix, gain_flat ? nullptr : e->d_gain, gain[0], e->dv_out,
+                                                         nframes, e->d_counters, e->dv_counters, SKB_N_COUNTERS, e->d_fin_ticket,
+                                                         e->dv_flag, seq);
+    e->stats.kernel_launches++;
+    e->stats.d2h_bytes += (uint64_t)nframes * sizeof(float2) + SKB_N_COUNTERS * sizeof(unsigned long long);
+    t_f1 = host_now_us();
+    /* poll the flag; every few thousand reads ask the stream, so that a failed launch ends the wait with its error */
+    unsigned int spins = 0;
+    cudaError_t qs = cudaErrorNotReady;
+    while (*e->h_flag != seq) {
+      if ((++spins & 0xfffu) == 0u) {
+        qs = cudaStreamQuery(st);
+        if (qs != cudaErrorNotReady) break;
+      }
+    }
+    if (*e->h_flag != seq) {                       /* the stream ended (or failed) before we saw the flag */
+      CK(qs == cudaErrorNotReady ? cudaSuccess : qs);
+      CK(cudaStreamSynchronize(st));
+      if (*e->h_flag != seq) return fail(e, SKB_ERR_CUDA, "finish: the completion flag was not written");
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    t_f2 = host_now_us();
+  } else {
+    k_finish<<<(nframes + 255) / 256, 256, 0, st>>>((const float2 *)d_mix, e->d_gain, e->d_out, nframes);
+    e->stats.kernel_launches++;
+    CK(cudaMemcpyAsync(e->h_out, e->d_out, (size_t)nframes * sizeof(float2), cudaMemcpyDeviceToHost, st));
+    e->stats.d2h_bytes += (uint64_t)nframes * sizeof(float2) + SKB_N_COUNTERS * sizeof(unsigned long long);
+    CK(cudaMemcpyAsync(e->h_counters, e->d_counters, SKB_N_COUNTERS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    t_f1 = host_now_us();
+    CK(cudaStreamSynchronize(st));
+    t_f2 = host_now_us();
+  }
   e->stats.host_us[1] += t_f1 - t_f0; e->stats.host_us[2] += t_f2 - t_f1;
   e->stats.active_voice_frames = e->h_counters[0] + e->h_counters[1];
   for (int i = 0; i < 8; i++) e->stats.class_rows[i] = e->h_counters[2 + i];

@@ -773,6 +773,35 @@ __global__ void k_finish(const float2 *__restrict__ mix, const float *__restrict
   }
 }
 
+/* The same, straight into the HOST's buffers (round 2, session 3): `out`, `counters_out` and `flag` are pinned host memory
+ * mapped into the device's address space, so the scaled frames and the engine's counters cross PCIe as the kernel's own
+ * posted writes — no device staging buffer, no two device-to-host copies queued behind the kernel, no stream
+ * synchronisation: the last block to finish (ticket) publishes `seq` in `flag` after a system-wide fence, and the host,
+ * which polls that word, finds every frame in place when it sees it.  `gain` = the per-frame trace, or nullptr for the
+ * usual case of a master volume that sits on its fixed point (`gain_const`; the products are the same either way). */
+__global__ void k_finish_host(const float2 *__restrict__ mix, const float *__restrict__ gain, float gain_const,
+                              float2 *__restrict__ out, int nframes,
+                              const unsigned long long *__restrict__ counters, unsigned long long *__restrict__ counters_out,
+                              int ncounters, unsigned int *ticket, volatile unsigned int *flag, unsigned int seq) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < nframes) {
+    const float2 m = mix[f];
+    const float g = gain ? gain[f] : gain_const;
+    out[f] = make_float2(m.x * g, m.y * g);
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < ncounters) counters_out[threadIdx.x] = counters[threadIdx.x];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    if (t == gridDim.x - 1) {
+      *ticket = 0u;
+      __threadfence_system();
+      *flag = seq;
+    }
+  }
+}
+
 /* ======================================================================== */
 /* K3  state edits at a block boundary                                       */
 /* ======================================================================== */

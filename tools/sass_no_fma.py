@@ -2,11 +2,11 @@
 """Parity guard for the packed fp32 ops (free_kernel.cuh, SKB_F32X2): ptxas contracts mul.rn.f32x2 -> add.rn.f32x2 into
 FFMA2 even under --fmad=false, which would round once where the reference rounds twice.  This tool disassembles the built
 engine and checks, per function, that (1) no FFMA2 exists at all and (2) the number of scalar FFMA (they come from the IEEE
-division / sqrt sequences of -prec-div=true and are the same ones the scalar build has) equals the count in the scalar build
-(-DSKB_F32X2=0, the default).
+division / sqrt sequences of -prec-div=true and are the same ones the scalar build has) equals the count in the all-scalar build.
 
-  python tools/sass_no_fma.py            # builds skred_b200/variants/x2 (-DSKB_F32X2=1), compares with the default (scalar)
-                                         # build, exits 1 on a difference
+  python tools/sass_no_fma.py [--all]    # the default build (mix pairs packed) — or, --all, skred_b200/variants/x2
+                                         # (-DSKB_F32X2=1: every pair) — against skred_b200/variants/scalar
+                                         # (-DSKB_F32X2_MIX=0); exits 1 on a difference
 """
 import collections
 import os
@@ -32,8 +32,9 @@ def counts(so):
 
 
 def main():
-    eng = B.build_engine_variant("x2", ["-DSKB_F32X2=1"])
-    ref = B.build_engine()          # the default build is the scalar one (SKB_F32X2 = 0)
+    full = "--all" in sys.argv      # check the build with EVERY pair packed (-DSKB_F32X2=1) instead of the default one
+    eng = B.build_engine_variant("x2", ["-DSKB_F32X2=1"]) if full else B.build_engine()
+    ref = B.build_engine_variant("scalar", ["-DSKB_F32X2_MIX=0"])          # no packed op anywhere
     a, b = counts(eng), counts(ref)
     bad = 0
     for fn in sorted(a):
