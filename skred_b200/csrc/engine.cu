@@ -866,7 +866,16 @@ static int replan(skb_engine *e, cudaStream_t st) {
     /* Rows -> CTAs, balanced by estimated cost (LPT: costliest row first, to the least loaded
      * CTA).  One CTA per SM; a CTA renders its rows in batches of SKB_CTA_WARPS, all rows of a
      * batch concurrently, so its time is roughly (sum of row costs) / issue rate. */
-    static const int cost_of_rank[8] = {0, 20, 24, 29, 36, 36, 46, 160};   /* instructions per voice-frame, measured */
+#ifndef SKB_COST_R4
+#define SKB_COST_R4 36
+#endif
+#ifndef SKB_COST_R6
+#define SKB_COST_R6 46
+#endif
+#ifndef SKB_COST_ONESHOT_DIV
+#define SKB_COST_ONESHOT_DIV 4
+#endif
+    static const int cost_of_rank[8] = {0, 20, 24, 29, SKB_COST_R4, 36, SKB_COST_R6, 160};   /* instructions per voice-frame, measured */
     const int nrows = e->n_free_rows;
     std::vector<int> row_rank((size_t)nrows, 0), row_cost((size_t)nrows, 0);
     std::vector<uint8_t> row_wide((size_t)nrows, 0), row_filt((size_t)nrows, 0);
@@ -885,7 +894,7 @@ static int replan(skb_engine *e, cudaStream_t st) {
           const uint64_t key = feature_key(&e->par[v]);
           rank = (int)((key >> SKB_KEY_CLASS_SHIFT) & 7);
           cost = cost_of_rank[rank];
-          if (e->par[v].flags & SKB_F_ONE_SHOT) cost = (cost + 3) / 4;      /* one-shots are mostly over; the kernel packs the rest */
+          if (e->par[v].flags & SKB_F_ONE_SHOT) cost = (cost + SKB_COST_ONESHOT_DIV - 1) / SKB_COST_ONESHOT_DIV;      /* one-shots are mostly over; the kernel packs the rest */
         }
       }
       row_rank[r] = rank; row_cost[r] = cost;
