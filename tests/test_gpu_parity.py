@@ -6,6 +6,7 @@ float difference allowed by design is the ORDER of the cross-voice sum
 (DESIGN.md §Mix); everything per-voice is computed with the reference's own
 individually rounded IEEE ops.
 """
+import ctypes as C
 import os
 
 import numpy as np
@@ -285,6 +286,32 @@ def test_run_to_run_deterministic(luts):
         _queue(s, wl["timed"])
         outs.append(s.render(3 * 4096, block=4096))
     assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+
+
+def test_direct_finish_equals_staged_finish(luts, monkeypatch):
+    """skb_finish writes the frames straight into mapped host memory and the host polls a flag (k_finish_host); with
+    SKB_FINISH_COPY=1 it stages them on the device and copies (k_finish + cudaMemcpyAsync + stream synchronise).  Same
+    products, same bits — ragged call sizes and a master-volume change included (a trace that is not flat takes the
+    per-frame gain path of k_finish_host)."""
+    from skred_b200 import workloads as W
+    wl = W.config5(1024, seconds=600.0, luts=luts, event_seconds=1.0, stationary=True)
+    outs, stats = [], []
+    for staged in (False, True):
+        if staged:
+            monkeypatch.setenv("SKB_FINISH_COPY", "1")
+        s = O.DropinCuda(1024, run_seq=False)
+        W.install(s, wl)
+        _queue(s, wl["timed"])
+        parts = [s.render(4096, block=4096), s.render(1500, block=700)]
+        s.lib.volume_set.argtypes = [C.c_float]
+        s.lib.volume_set(0.37)                             # the one-pole of the master volume starts moving
+        parts += [s.render(2 * 4096, block=4096), s.render(3, block=3)]
+        outs.append(np.concatenate(parts))
+        stats.append(s.engine_stats().active_voice_frames)
+    monkeypatch.delenv("SKB_FINISH_COPY")
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+    assert stats[0] == stats[1] and stats[0] > 0
+    assert float(np.abs(outs[0]).max()) > 1e-3
 
 
 @pytest.mark.parametrize("which", ["config5_events", "korg_filter", "pcm_dense", "lut_release"])
