@@ -216,6 +216,11 @@ int  skb_render_mix(skb_engine *e, int nframes, uint64_t ssc_before,
  * skb_snapshot do so implicitly.  Call it before consuming d_mix on the stream yourself
  * (e.g. before an NCCL reduce). */
 int  skb_flush(skb_engine *e);
+/* skb_finish applies the master-volume trace gain[nframes] (host memory, synth.c:619-624) to d_mix and returns the frames in
+ * the HOST buffer `out`; blocking.  The finishing kernel writes the engine's pinned host buffer directly (mapped into the
+ * device's address space) and raises a flag the call polls: no device-to-host copy, no stream synchronisation.  Environment:
+ * SKB_FINISH_COPY=1 at skb_create selects the staged form (device buffer, cudaMemcpyAsync, cudaStreamSynchronize) — the same
+ * bits (tests: test_direct_finish_equals_staged_finish). */
 int  skb_finish(skb_engine *e, const float *d_mix, int nframes, const float *gain,
                 float *out, int num_channels, void *stream);
 /* The engine's own raw-mix buffer (DEVICE memory, max_frames x 2 floats) for callers of the
