@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(RP_THREADS) k_render_levels(const __grid_const
         renders = (__float_as_int(s0.y) == 0) && (amp != 0.0f);
         woken = a.wake != nullptr && ((__ldg(a.wake + (slot >> 5)) >> (slot & 31)) & 1u);
         if (roleA && my_tro >= 0) trace[(size_t)my_tro * tstride] = s0.z;
-        if (roleA && !renders && s0.z != 0.0f) { s0.z = 0.0f; sq[slot] = s0; }
+        if (roleA && !renders && __float_as_uint(s0.z) != 0u) { s0.z = 0.0f; sq[slot] = s0; }
       }
       const bool any = __any_sync(0xffffffffu, renders || woken);
       __syncthreads();                                                /* (the zeroed samples are visible to every warp) */

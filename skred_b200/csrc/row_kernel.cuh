@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(RP_THREADS) k_render_rows(const __grid_constan
       float4 s0 = sq[slot];
       renders = (__float_as_int(s0.y) == 0) && (amp != 0.0f);
       woken = a.wake != nullptr && ((__ldg(a.wake + (slot >> 5)) >> (slot & 31)) & 1u);
-      if (roleA && !renders && s0.z != 0.0f) { s0.z = 0.0f; sq[slot] = s0; }      /* skipped voice: voice_sample = 0, :534,540 */
+      if (roleA && !renders && __float_as_uint(s0.z) != 0u) { s0.z = 0.0f; sq[slot] = s0; }      /* skipped voice: voice_sample = 0, :534,540 */
     }
     if (!__any_sync(0xffffffffu, renders || woken)) {
       for (int f = tid; f < a.nframes; f += RP_THREADS) orow[f] = make_float2(0.0f, 0.0f);
