@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(RP_THREADS) k_render_levels(const __grid_const
       bool dyn = false;
       int filt = 0;
       if (roleC) {
-        const bool stn = !varying && (fs.g + c.sm_k * (c.gc - fs.g) == fs.g);
+        const bool stn = !varying && smoother_settled(fs.g, c.sm_k, c.gc);
         dyn = !__all_sync(0xffffffffu, stn);
         const bool anyf = __any_sync(0xffffffffu, c.has_f), allf = __all_sync(0xffffffffu, c.has_f || dead);
         filt = !anyf ? 0 : (allf ? 1 : 2);
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(RP_THREADS) k_render_levels(const __grid_const
                   default: rp_out_block<2, 1>(S, bi, nf, c, fs, lane); break;
                 }
                 if (!has_rows) {
-                  const bool stn = (fs.g + c.sm_k * (c.gc - fs.g) == fs.g);
+                  const bool stn = smoother_settled(fs.g, c.sm_k, c.gc);
                   dyn = !__all_sync(0xffffffffu, stn);
                 }
               } else {

@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(RP_THREADS) k_render_rows(const __grid_constan
         if (varying) S.er[lane] = er;
         const unsigned vm = __ballot_sync(0xffffffffu, varying);
         if (lane == 0) S.varmask = vm;
-        const bool st = !varying && (fs.g + c.sm_k * (c.gc - fs.g) == fs.g);     /* smoother on its fixed point: not stepped */
+        const bool st = !varying && smoother_settled(fs.g, c.sm_k, c.gc);     /* smoother on its fixed point: not stepped */
         dyn = !__all_sync(0xffffffffu, st);
         const bool anyf = __any_sync(0xffffffffu, c.has_f), allf = __all_sync(0xffffffffu, c.has_f || dead);
         filt = !anyf ? 0 : (allf ? 1 : 2);
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(RP_THREADS) k_render_rows(const __grid_constan
                   default: rp_out_block<2, 1>(S, bi, nf, c, fs, lane); break;
                 }
                 if (!has_rows) {                                      /* every smoother settled on its constant target? */
-                  const bool st = (fs.g + c.sm_k * (c.gc - fs.g) == fs.g);
+                  const bool st = smoother_settled(fs.g, c.sm_k, c.gc);
                   dyn = !__all_sync(0xffffffffu, st);
                 }
               } else {

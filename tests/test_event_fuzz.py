@@ -19,7 +19,7 @@ EXACT = ("phase", "finished", "sh_hold", "sh_count", "env_active", "env_start", 
          "sample", "filter_xy", "smoother_gain", "pan_left", "pan_right")
 
 
-def random_events(rng, frames, n):
+def random_events(rng, frames, n, neg_amp=False):
     waves = [0, 1, 2, 3, 4, 5, 33, 40, 47, 62, 100, 111, 140, 166, 200, 201, 202]
     out = []
     for _ in range(n):
@@ -35,7 +35,8 @@ def random_events(rng, frames, n):
         elif k == 7:
             c = ("freq_midi", v, float(rng.randint(30, 90)))
         elif k == 8:
-            c = ("amp_set", v, float(np.float32(rng.choice([0.0, 0.02, 0.04]))))
+            # (neg_amp: negative amplitudes too — gains and smoother states of either sign, zeros of either sign once they decay)
+            c = ("amp_set", v, float(np.float32(rng.choice([0.0, 0.02, -0.03, 0.04] if neg_amp else [0.0, 0.02, 0.04]))))
         elif k == 9:
             c = ("pan_set", v, float(np.float32(rng.uniform(-1.0, 1.0))))
         elif k == 10:
@@ -58,10 +59,10 @@ def _calls_for_reference(timed):
     return ev
 
 
-def run(seed, make_dut, luts, frames=5 * 4096 + 700, n_events=2500, call=4096):
+def run(seed, make_dut, luts, frames=5 * 4096 + 700, n_events=2500, call=4096, neg_amp=False):
     rng = np.random.RandomState(seed)
     wl = W.config5(V, seconds=600.0, luts=luts, event_seconds=frames / 44100.0 + 1.0, stationary=True)
-    timed = sorted(wl["timed"] + random_events(rng, frames, n_events), key=lambda x: x[0])
+    timed = sorted(wl["timed"] + random_events(rng, frames, n_events, neg_amp), key=lambda x: x[0])
     ref, dut = O.RefSkred(V, run_seq=False), make_dut(V, run_seq=False)
     W.install(ref, wl)
     W.install(dut, wl)
@@ -94,3 +95,13 @@ def test_random_event_stream_cuda_vs_reference(seed, call, luts):
     dut = run(seed, O.DropinCuda, luts, call=call)
     st = dut.engine_stats()
     assert st.ops_applied > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,call", [(21, 4096), (22, 1536)])
+def test_random_event_stream_negative_amps_cuda_vs_reference(seed, call, luts):
+    """The same with negative amplitudes in the stream and a render long enough for released voices' smoothers to decay into
+    the denormals: state words of either sign, zeros included (the DYN = 0 shortcut and the voice_sample reset compare bits)."""
+    if not O.have_ref(V):
+        pytest.skip("compiled reference for 1,024 voices not present")
+    run(seed, O.DropinCuda, luts, frames=9 * 4096 + 300, n_events=3000, call=call, neg_amp=True)
