@@ -90,7 +90,8 @@ def test_random_event_stream_shim_queue_vs_reference_callbacks(seed, luts):
 #  tools/gpu_event_fuzz_sweep.py 300 60 at the end of round 2, 18 of 60 seeds, one word each.
 #  2015, 2149: a `wave_set` to a one-shot table right before the last callback — finished latch set by an op at a launch's first
 #  boundary, after the compaction's skip rule had run: voice_sample kept its last value instead of 0; 4 of 200 seeds)
-@pytest.mark.parametrize("seed,call", [(11, 4096), (12, 4096), (13, 8192), (14, 512), (15, 1536), (16, 4096), (303, 1536), (332, 512), (2015, 4096), (2149, 8192)])
+@pytest.mark.parametrize("seed,call", [(11, 4096), (12, 4096), (13, 8192), (14, 512), (15, 1536), (16, 4096), (303, 1536), (332, 512), (2015, 4096), (2149, 8192),
+                                       (2142, 4096), (2148, 4096), (2001, 1536), (2002, 2048), (2005, 8192), (2006, 512)])
 def test_random_event_stream_cuda_vs_reference(seed, call, luts):
     if not O.have_ref(V):
         pytest.skip("compiled reference for 1,024 voices not present")
